@@ -1,0 +1,99 @@
+// Shared declarations of libvapb200 (B200 / sm_100a VAP streaming step).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace vapb {
+
+constexpr int kD = 256;        // model width            (rvap/vap_main/vap_main.py:50)
+constexpr int kFF = 768;       // FFN width, dff_k = 3   (vap_main.py:110)
+constexpr int kHeads = 4;      // heads                  (vap_main.py:53)
+constexpr int kHeadDim = 64;
+constexpr int kPadSamples = 320;   // frame_contxt_padding (vap_main.py:224)
+constexpr int kMaxT = 128;     // largest supported window (frames)
+constexpr float kEps = 1e-5f;
+
+// Affine row addressing used for activations that are stored per audio chunk
+// with zero "halo" rows (the conv padding materialised once at allocation):
+//   element offset of logical row r = offset + (r / rpc) * chunk_stride + (r % rpc) * row_stride
+// A plain [M, ld] matrix is {rpc = 1<<30, chunk_stride = 0, row_stride = ld, offset = 0}.
+struct RowMap {
+    int rpc;
+    long long chunk_stride;
+    long long row_stride;
+    long long offset;
+};
+
+__host__ __device__ inline long long rowmap_off(const RowMap& m, int r) {
+    return m.offset + (long long)(r / m.rpc) * m.chunk_stride + (long long)(r % m.rpc) * m.row_stride;
+}
+
+inline RowMap plain_map(long long ld, long long offset = 0) {
+    RowMap m;
+    m.rpc = 1 << 30;
+    m.chunk_stride = 0;
+    m.row_stride = ld;
+    m.offset = offset;
+    return m;
+}
+
+struct GemmArgs {
+    const float* A;
+    RowMap amap;          // row m of A (K contiguous floats)
+    const float* W;       // [N][K] row major (K contiguous): C = A * W^T
+    const float* bias;    // [N] or nullptr
+    const float* R;       // residual added after the activation, or nullptr
+    RowMap rmap;
+    float* C;
+    RowMap cmap;
+    int M, N, K;
+    int act;              // 0 = none, 1 = exact-erf GELU
+};
+
+// ---- launchers implemented in kernels_simt.cu -------------------------------------------
+void launch_conv0(const float* audio, int n_chunks, int S, int L0, const float* w, const float* b,
+                  const float* cnw, const float* cnb, float* out, RowMap omap, cudaStream_t st);
+void launch_sgemm(const GemmArgs& g, cudaStream_t st);
+void launch_cn_relu(float* X, RowMap map, int M, const float* w, const float* b, cudaStream_t st);
+void launch_layernorm(const float* X, RowMap xmap, float* Y, RowMap ymap, int M, const float* w,
+                      const float* b, int gelu, cudaStream_t st);
+void launch_gather_state(const float* hS, const float* cS, const int* ids, float* hW, float* cW, int B,
+                         cudaStream_t st);
+void launch_scatter_state(float* hS, float* cS, const int* ids, const float* hW, const float* cW, int B,
+                          cudaStream_t st);
+void launch_lstm_cell(const float* G, float* hW, float* cW, float* Y, int n_rows, int n_steps, int step,
+                      cudaStream_t st);
+void launch_ln_gelu_ring(const float* X, int B, const float* w, const float* b, float* ring,
+                         const int* count, const int* ids, int T, float* e_out, cudaStream_t st);
+void launch_gather_ring(const float* ring, const int* count, const int* ids, float* X, int* tvalid, int B,
+                        int T, cudaStream_t st);
+struct AttnArgs {
+    const float* Q; int ldq;       // row r, head h at Q + r*ldq + h*64
+    const float* K; int ldk;
+    const float* V; int ldv;
+    float* O; int ldo;
+    const int* tvalid;             // [B] valid rows per stream
+    const float* slopes;           // [4] ALiBi m_h
+    int n_seq;                     // 2B sequences of T rows each
+    int T;
+    int sibling;                   // 1: K/V rows come from the other channel of the same stream
+};
+void launch_attention(const AttnArgs& a, cudaStream_t st);
+void launch_vad(const float* X, const int* tvalid, const float* w, const float* b, float* out, int B, int T,
+                cudaStream_t st);
+struct HeadArgs {
+    const float* X;            // [2B*T][256] final cross-layer output
+    const int* tvalid;
+    const float* Wa; const float* Wb; const float* lnw; const float* lnb;
+    const float* Wh; const float* bh; int n_out;   // 256 (vap) or 3 (bc)
+    float* out;                // [B][6]
+    float* comb_tap;           // [B][256] or nullptr
+    float* logits_tap;         // [B][256] or nullptr
+    int* count; const int* ids;
+    int B, T, head_kind;
+};
+void launch_head(const HeadArgs& a, cudaStream_t st);
+
+}  // namespace vapb

@@ -1,0 +1,509 @@
+// tcgen05 bf16x3 GEMM for sm_100a -- see gemm_tc.cuh for the scheme.
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+//   warps 0-3  A producers: fp32 global -> (hi, lo) bf16 -> swizzled smem; afterwards the
+//              epilogue (tcgen05.ld of "their" 32 TMEM lanes -> bias/GELU/residual -> global)
+//   warp 4     TMA producer for the two W planes (cp.async.bulk.tensor, 128B swizzle)
+//   warp 5     TMEM allocator + the single thread that issues tcgen05.mma
+// Pipelines: smem full/empty mbarriers per stage, one "accumulator ready" mbarrier.
+#include "gemm_tc.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace vapb {
+
+namespace {
+
+constexpr int kBM = 128;          // rows per CTA tile = UMMA M
+constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 192;
+constexpr int kATile = kBM * kBK * 2;     // bytes per A plane per stage (16 KB)
+
+template <int BN>
+struct Cfg {
+    static constexpr int kWTile = BN * kBK * 2;                       // bytes per W plane per stage
+    static constexpr int kStageBytes = 2 * kATile + 2 * kWTile;
+    static constexpr int kStages = (BN == 256) ? 2 : 3;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a mis-programmed pipeline must fail loudly (trap -> launch failure), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("vapb gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (= 1, unused for swizzled K-major)
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BN.
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+// ---- the kernel -----------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024 B alignment
+    const uint32_t bars = base + C::kStages * C::kStageBytes;
+    // barrier slots: full[s] at bars + 8*s, empty[s] at bars + 8*(kStages+s), accum at bars + 16*kStages, tmem ptr after
+    const uint32_t bar_accum = bars + 16 * C::kStages;
+    const uint32_t tmem_slot = bar_accum + 8;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::kStages + s); };
+    auto a_hi = [&](int s) { return base + (uint32_t)s * C::kStageBytes; };
+    auto a_lo = [&](int s) { return a_hi(s) + kATile; };
+    auto w_hi = [&](int s) { return a_hi(s) + 2 * kATile; };
+    auto w_lo = [&](int s) { return w_hi(s) + C::kWTile; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+    const int nkb = g.K / kBK;
+
+    if (warp == 4 && lane == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(full_bar(s), 4 + 1);       // 4 producer warps + the TMA thread's expect_tx arrive
+            mbar_init(empty_bar(s), 1);          // one tcgen05.commit
+        }
+        mbar_init(bar_accum, 1);
+        fence_barrier_init();
+        prefetch_tmap(&map_hi);
+        prefetch_tmap(&map_lo);
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp < 4) {
+        // ================= A producers =================
+        const int chunk = tid & 7;                     // 16-byte chunk (8 bf16) within the 128-byte row
+        const int r0 = tid >> 3;                       // rows r0 + 16*i
+        const float* rowp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + r0 + 16 * i;
+            rowp[i] = (m < g.M) ? (g.A + rowmap_off(g.amap, m) + chunk * 8) : nullptr;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % C::kStages;
+            const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
+            float4 v[8][2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (rowp[i]) {
+                    const float4* p = reinterpret_cast<const float4*>(rowp[i] + (size_t)kb * kBK);
+                    v[i][0] = __ldg(p);
+                    v[i][1] = __ldg(p + 1);
+                } else {
+                    v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i][1] = v[i][0];
+                }
+            }
+            mbar_wait(empty_bar(s), ph ^ 1u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 16 * i;
+                uint32_t h[4], l[4];
+                split2(v[i][0].x, v[i][0].y, h[0], l[0]);
+                split2(v[i][0].z, v[i][0].w, h[1], l[1]);
+                split2(v[i][1].x, v[i][1].y, h[2], l[2]);
+                split2(v[i][1].z, v[i][1].w, h[3], l[3]);
+                const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(chunk ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi(s) + off), "r"(h[0]), "r"(h[1]), "r"(h[2]),
+                             "r"(h[3])
+                             : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo(s) + off), "r"(l[0]), "r"(l[1]), "r"(l[2]),
+                             "r"(l[3])
+                             : "memory");
+            }
+            fence_proxy_async();                      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));
+        }
+        // ================= epilogue =================
+        mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        const int m = m0 + warp * 32 + lane;           // TMEM lane == accumulator row
+        const bool valid = m < g.M;
+        float* crow = valid ? (g.C + rowmap_off(g.cmap, m)) : nullptr;
+        const float* rrow = (valid && g.R) ? (g.R + rowmap_off(g.rmap, m)) : nullptr;
+#pragma unroll 1
+        for (int cb = 0; cb < BN / 32; ++cb) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), raw);
+            if (valid) {
+                const int n = n0 + cb * 32;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float x[4] = {__uint_as_float(raw[4 * q + 0]), __uint_as_float(raw[4 * q + 1]),
+                                  __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3])};
+                    if (g.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4 * q));
+                        x[0] += bb.x; x[1] += bb.y; x[2] += bb.z; x[3] += bb.w;
+                    }
+                    if (g.act == 1) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x[e] = gelu_erf(x[e]);
+                    }
+                    if (rrow) {
+                        const float4 rr = *reinterpret_cast<const float4*>(rrow + n + 4 * q);
+                        x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+                    }
+                    *reinterpret_cast<float4*>(crow + n + 4 * q) = make_float4(x[0], x[1], x[2], x[3]);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================= TMA producer (W planes) =================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::kStages;
+                const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), 2u * C::kWTile);
+                tma_load_2d(w_hi(s), &map_hi, kb * kBK, n0, full_bar(s));
+                tma_load_2d(w_lo(s), &map_lo, kb * kBK, n0, full_bar(s));
+            }
+        }
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::kStages;
+                const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                    const uint32_t koff = (uint32_t)k * kUmmaK * 2;          // bytes along K inside the swizzle row
+                    const uint64_t ah = make_desc(a_hi(s) + koff), al = make_desc(a_lo(s) + koff);
+                    const uint64_t wh = make_desc(w_hi(s) + koff), wl = make_desc(w_lo(s) + koff);
+                    umma_bf16(tmem_base, al, wh, idesc, (kb | k) ? 1u : 0u);   // small terms first
+                    umma_bf16(tmem_base, ah, wl, idesc, 1u);
+                    umma_bf16(tmem_base, ah, wh, idesc, 1u);
+                }
+                umma_commit(empty_bar(s));            // frees the stage when these MMAs have read it
+            }
+            umma_commit(bar_accum);                   // accumulator complete
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, BN);
+}
+
+// fp32 [n] -> bf16 hi / lo planes
+__global__ void k_split_planes(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn(std::string& err) {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+        err = std::string("cuTensorMapEncodeTiled not available: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+bool encode_plane(CUtensorMap* map, void* ptr, int N, int K, int box_n, std::string& err) {
+    EncodeTiledFn fn = get_encode_fn(err);
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_n};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
+int pick_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+
+template <int BN>
+bool ensure_attr(std::string* err) {
+    static bool done = false;
+    if (done) return true;
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) {
+        if (err) *err = std::string("cudaFuncSetAttribute(k_gemm_tc) failed: ") + cudaGetErrorString(e);
+        return false;
+    }
+    done = true;
+    return true;
+}
+
+}  // namespace
+
+bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vector<void*>& allocs, std::string& err) {
+    if (!W_dev) {
+        err = "tc_prepare_weight: null weight";
+        return false;
+    }
+    if (K % kBK != 0 || N % 128 != 0) {
+        err = "tc_prepare_weight: unsupported shape";
+        return false;
+    }
+    const size_t n = (size_t)N * K;
+    void *hi = nullptr, *lo = nullptr;
+    if (cudaMalloc(&hi, n * 2) != cudaSuccess || cudaMalloc(&lo, n * 2) != cudaSuccess) {
+        err = "cudaMalloc failed (bf16 weight planes)";
+        return false;
+    }
+    allocs.push_back(hi);
+    allocs.push_back(lo);
+    out.hi = static_cast<__nv_bfloat16*>(hi);
+    out.lo = static_cast<__nv_bfloat16*>(lo);
+    out.N = N;
+    out.K = K;
+    out.block_n = pick_block_n(N);
+    k_split_planes<<<(unsigned)((n + 255) / 256), 256>>>(W_dev, out.hi, out.lo, n);
+    if (cudaGetLastError() != cudaSuccess) {
+        err = "k_split_planes launch failed";
+        return false;
+    }
+    if (!encode_plane(&out.map_hi, hi, N, K, out.block_n, err)) return false;
+    if (!encode_plane(&out.map_lo, lo, N, K, out.block_n, err)) return false;
+    if (!ensure_attr<128>(&err) || !ensure_attr<256>(&err)) return false;
+    return true;
+}
+
+bool tc_prepare_workspace(TcWorkspace&, size_t, std::vector<void*>&, std::string&) { return true; }
+
+int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace&, cudaStream_t st) {
+    dim3 grid((g.M + kBM - 1) / kBM, g.N / w.block_n);
+    if (w.block_n == 256)
+        k_gemm_tc<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(g, w.map_hi, w.map_lo);
+    else
+        k_gemm_tc<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(g, w.map_hi, w.map_lo);
+    return 1;
+}
+
+// ---- self test --------------------------------------------------------------------------
+int tc_selftest(int device, int variant, double* max_rel_err, std::string& report) {
+    struct Case { int M, N, K; int conv; int bias, act, resid; };
+    // conv: A is a channels-last chunked view with overlapping rows (conv1 geometry: k=8, s=4, pad=2, L 224 -> 56)
+    static const Case cases[] = {
+        {300, 256, 256, 0, 0, 0, 0},
+        {1000, 768, 256, 0, 1, 1, 0},
+        {7 * 56, 256, 2048, 1, 1, 0, 0},
+        {640, 512, 768, 0, 0, 0, 1},
+        {129, 256, 1280, 0, 1, 0, 1},
+        {6400, 256, 768, 0, 0, 0, 1},
+    };
+    const int ncases = (int)(sizeof(cases) / sizeof(cases[0]));
+    if (variant < 0 || variant >= ncases) {
+        report = "variant out of range";
+        return -1;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        report = "cudaSetDevice failed";
+        return -2;
+    }
+    const Case cs = cases[variant];
+    const int M = cs.M, N = cs.N, K = cs.K;
+    RowMap amap = plain_map(K);
+    size_t a_elems = (size_t)M * K;
+    if (cs.conv) {
+        const int chunks = M / 56, rows = 224 + 4;
+        a_elems = (size_t)chunks * rows * 256;
+        amap.rpc = 56;
+        amap.chunk_stride = (long long)rows * 256;
+        amap.row_stride = 4 * 256;
+        amap.offset = 0;
+    }
+    std::vector<float> hA(a_elems), hW((size_t)N * K), hb(N), hR((size_t)M * N);
+    uint32_t sd = 12345u + 77u * variant;
+    auto rnd = [&]() {
+        sd = sd * 1664525u + 1013904223u;
+        return ((sd >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+    };
+    for (auto& x : hA) x = rnd();
+    for (auto& x : hW) x = rnd() * 0.1f;
+    for (auto& x : hb) x = rnd();
+    for (auto& x : hR) x = rnd();
+    float *dA, *dW, *db, *dR, *dC0, *dC1;
+    std::vector<void*> allocs;
+    auto al = [&](float** p, size_t n) {
+        cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(float));
+        allocs.push_back(*p);
+    };
+    al(&dA, a_elems); al(&dW, hW.size()); al(&db, N); al(&dR, hR.size()); al(&dC0, hR.size()); al(&dC1, hR.size());
+    cudaMemcpy(dA, hA.data(), a_elems * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, hW.data(), hW.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, hb.data(), N * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dR, hR.data(), hR.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dC0, 0, hR.size() * 4);
+    cudaMemset(dC1, 0xFF, hR.size() * 4);
+    TcWeight tw;
+    std::string err;
+    int rc = 0;
+    if (!tc_prepare_weight(dW, N, K, tw, allocs, err)) {
+        report = err;
+        rc = -3;
+    }
+    if (!rc) {
+        GemmArgs g;
+        g.A = dA; g.amap = amap; g.W = dW; g.bias = cs.bias ? db : nullptr; g.R = cs.resid ? dR : nullptr;
+        g.rmap = plain_map(N); g.C = dC0; g.cmap = plain_map(N); g.M = M; g.N = N; g.K = K; g.act = cs.act;
+        launch_sgemm(g, 0);
+        g.C = dC1;
+        TcWorkspace ws;
+        launch_gemm_tc(g, tw, ws, 0);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            report = std::string("kernel failed: ") + cudaGetErrorString(e);
+            rc = -4;
+        }
+    }
+    if (!rc) {
+        std::vector<float> c0(hR.size()), c1(hR.size());
+        cudaMemcpy(c0.data(), dC0, c0.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(c1.data(), dC1, c1.size() * 4, cudaMemcpyDeviceToHost);
+        double maxabs = 0, maxdiff = 0;
+        size_t worst = 0, nbad = 0;
+        for (size_t i = 0; i < c0.size(); ++i) {
+            maxabs = std::max(maxabs, (double)std::fabs(c0[i]));
+            double d = std::fabs((double)c0[i] - (double)c1[i]);
+            if (!(d == d)) { d = 1e30; }
+            if (d > maxdiff) { maxdiff = d; worst = i; }
+            if (d > 1e-3) ++nbad;
+        }
+        *max_rel_err = maxdiff / std::max(maxabs, 1e-30);
+        char buf[512];
+        snprintf(buf, sizeof buf,
+                 "variant %d M=%d N=%d K=%d BN=%d: max|ref|=%.4g max|diff|=%.4g rel=%.3g nbad=%zu worst@(%zu,%zu) ref=%.6g tc=%.6g; "
+                 "C[0][0..3] ref=%.5g %.5g %.5g %.5g tc=%.5g %.5g %.5g %.5g",
+                 variant, M, N, K, tw.block_n, maxabs, maxdiff, *max_rel_err, nbad, worst / N, worst % N, c0[worst], c1[worst],
+                 c0[0], c0[1], c0[2], c0[3], c1[0], c1[1], c1[2], c1[3]);
+        report = buf;
+    }
+    for (void* p : allocs) cudaFree(p);
+    return rc;
+}
+
+}  // namespace vapb

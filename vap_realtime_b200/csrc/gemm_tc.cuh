@@ -1,0 +1,49 @@
+// tcgen05 (5th-gen tensor core) GEMM with bf16 hi/lo split operands ("bf16 x3").
+//
+//   C[M,N] = act(A[M,K] * W[N,K]^T + bias) + R        fp32 in, fp32 out
+//
+// fp32 parity with the reference needs more than one bf16/tf32 product
+// (plain TF32 / BF16 miss the 1e-4 gate).  Every operand is split
+// as x = hi + lo (both bf16) and three MMAs accumulate into ONE fp32 TMEM tile:
+//   hi*hi + hi*lo + lo*hi       (the lo*lo term is below fp32 resolution)
+//  * W planes are split once at vapb_create and fetched with TMA (128B swizzle).
+//  * A stays fp32 in global memory; producer warps load it with coalesced 128-bit
+//    loads, split it in registers and store the two planes straight into the
+//    swizzled K-major smem layout the UMMA descriptors expect.  Because A rows are
+//    addressed through a RowMap, the Conv1d layers run im2col-free on the
+//    channels-last activations (overlapping rows, zero halo rows = padding).
+#pragma once
+
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <string>
+#include <vector>
+
+namespace vapb {
+
+struct TcWeight {
+    __nv_bfloat16* hi = nullptr;     // [N][K]
+    __nv_bfloat16* lo = nullptr;     // [N][K]
+    int N = 0, K = 0;
+    int block_n = 0;                 // N tile the tensor maps were encoded for
+    CUtensorMap map_hi, map_lo;      // 2D {K, N}, box {64, block_n}, SWIZZLE_128B
+};
+
+struct TcWorkspace {
+    int dummy = 0;
+};
+
+// Splits W (device fp32 [N][K]) into bf16 planes and encodes the TMA descriptors.
+bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vector<void*>& allocs, std::string& err);
+bool tc_prepare_workspace(TcWorkspace& ws, size_t max_a_elems, std::vector<void*>& allocs, std::string& err);
+
+// Enqueues the GEMM; returns the number of kernels launched.
+int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace& ws, cudaStream_t st);
+
+// Runs the tensor-core GEMM against the fp32 CUDA-core GEMM on random data.
+int tc_selftest(int device, int variant, double* max_rel_err, std::string& report);
+
+}  // namespace vapb

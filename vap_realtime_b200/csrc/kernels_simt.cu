@@ -1,0 +1,618 @@
+// CUDA-core (true fp32 FMA) kernels of the VAP streaming step.
+//
+// These are the precision-critical ops that must stay in fp32 (conv0, the LSTM
+// recurrence) plus the row-wise / attention / head kernels, and an
+// fp32 GEMM that serves as the exact-arithmetic mode of the library
+// (option "gemm"=0) against which the tcgen05 bf16x3 path is validated.
+//
+// Reference semantics restated per kernel (file:line under the reference tree).
+#include "common.cuh"
+
+#include <math.h>
+
+namespace vapb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+    // nn.GELU() default = exact erf form (modules.py:9-21, encoder_components.py:506)
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// -----------------------------------------------------------------------------------------
+// conv0 (1 -> 256, k=10, s=5, p=3) + ChannelNorm + ReLU, channels-last output.
+// encoder_components.py:83-84, 99 ; ChannelNorm :62-70 (unbiased variance, eps in rsqrt).
+// One warp per output position; lane owns channels {4*lane..4*lane+3, 128+4*lane..+3}.
+// -----------------------------------------------------------------------------------------
+constexpr int kC0PosPerBlock = 56;
+
+__global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__ audio, int S, int L0,
+                                                       const float* __restrict__ w,    // [256][10]
+                                                       const float* __restrict__ b,
+                                                       const float* __restrict__ cnw,
+                                                       const float* __restrict__ cnb,
+                                                       float* __restrict__ out, RowMap omap) {
+    __shared__ float s_in[kC0PosPerBlock * 5 + 16];
+    const int chunk = blockIdx.y;
+    const int p0 = blockIdx.x * kC0PosPerBlock;
+    const int npos = min(kC0PosPerBlock, L0 - p0);
+    const int first = 5 * p0 - 3;
+    const int need = 5 * (npos - 1) + 10;
+    const float* a = audio + (size_t)chunk * S;
+    for (int i = threadIdx.x; i < need; i += blockDim.x) {
+        int s = first + i;
+        s_in[i] = (s >= 0 && s < S) ? a[s] : 0.0f;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ch[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ch[i] = (i < 4) ? (lane * 4 + i) : (128 + lane * 4 + (i - 4));
+    float wr[8][10], br[8], gw[8], gb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) wr[i][k] = w[ch[i] * 10 + k];
+        br[i] = b[ch[i]];
+        gw[i] = cnw[ch[i]];
+        gb[i] = cnb[ch[i]];
+    }
+    __syncthreads();
+    for (int p = warp; p < npos; p += 8) {
+        float x[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) x[k] = s_in[5 * p + k];
+        float v[8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) acc = fmaf(wr[i][k], x[k], acc);
+            v[i] = acc + br[i];
+            s += v[i];
+        }
+        const float mean = warp_sum(s) * (1.0f / 256.0f);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float d = v[i] - mean;
+            q = fmaf(d, d, q);
+        }
+        const float var = warp_sum(q) * (1.0f / 255.0f);
+        const float rstd = 1.0f / sqrtf(var + kEps);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf((v[i] - mean) * rstd * gw[i] + gb[i], 0.0f);
+        float* dst = out + rowmap_off(omap, chunk * L0 + p0 + p);
+        *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dst + 128 + lane * 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+void launch_conv0(const float* audio, int n_chunks, int S, int L0, const float* w, const float* b,
+                  const float* cnw, const float* cnb, float* out, RowMap omap, cudaStream_t st) {
+    dim3 grid((L0 + kC0PosPerBlock - 1) / kC0PosPerBlock, n_chunks);
+    k_conv0_cn_relu<<<grid, 256, 0, st>>>(audio, S, L0, w, b, cnw, cnb, out, omap);
+}
+
+// -----------------------------------------------------------------------------------------
+// fp32 GEMM  C[M,N] = act(A[M,K] * W[N,K]^T + bias) + R     (both operands K-contiguous)
+// 128x128x8 tiles, 256 threads, 8x8 register block, smem double buffering.
+// N % 128 == 0, K % 8 == 0 (true for every shape on this path); M arbitrary.
+// -----------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 8, LDS = 132;
+
+__global__ void __launch_bounds__(256) k_sgemm(GemmArgs g) {
+    __shared__ __align__(16) float As[2][BK][LDS];
+    __shared__ __align__(16) float Bs[2][BK][LDS];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int lr = tid >> 1, kq = (tid & 1) * 4;
+    const int am = m0 + lr;
+    const float* aptr = (am < g.M) ? (g.A + rowmap_off(g.amap, am) + kq) : nullptr;
+    const float* wptr = g.W + (size_t)(n0 + lr) * g.K + kq;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ra = aptr ? __ldg(reinterpret_cast<const float4*>(aptr)) : z4;
+    float4 rw = __ldg(reinterpret_cast<const float4*>(wptr));
+    As[0][kq + 0][lr] = ra.x; As[0][kq + 1][lr] = ra.y; As[0][kq + 2][lr] = ra.z; As[0][kq + 3][lr] = ra.w;
+    Bs[0][kq + 0][lr] = rw.x; Bs[0][kq + 1][lr] = rw.y; Bs[0][kq + 2][lr] = rw.z; Bs[0][kq + 3][lr] = rw.w;
+    __syncthreads();
+
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int nk = g.K / BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int cur = kt & 1;
+        if (kt + 1 < nk) {
+            ra = aptr ? __ldg(reinterpret_cast<const float4*>(aptr + (size_t)(kt + 1) * BK)) : z4;
+            rw = __ldg(reinterpret_cast<const float4*>(wptr + (size_t)(kt + 1) * BK));
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            const int nx = cur ^ 1;
+            As[nx][kq + 0][lr] = ra.x; As[nx][kq + 1][lr] = ra.y; As[nx][kq + 2][lr] = ra.z; As[nx][kq + 3][lr] = ra.w;
+            Bs[nx][kq + 0][lr] = rw.x; Bs[nx][kq + 1][lr] = rw.y; Bs[nx][kq + 2][lr] = rw.z; Bs[nx][kq + 3][lr] = rw.w;
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4)));
+        if (m >= g.M) continue;
+        float* crow = g.C + rowmap_off(g.cmap, m);
+        const float* rrow = g.R ? (g.R + rowmap_off(g.rmap, m)) : nullptr;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int n = n0 + jj * 64 + tx * 4;
+            float v[4] = {acc[i][jj * 4 + 0], acc[i][jj * 4 + 1], acc[i][jj * 4 + 2], acc[i][jj * 4 + 3]};
+            if (g.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+            }
+            if (g.act == 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = gelu_erf(v[q]);
+            }
+            if (rrow) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow + n);
+                v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+            }
+            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+void launch_sgemm(const GemmArgs& g, cudaStream_t st) {
+    dim3 grid((g.M + BM - 1) / BM, g.N / BN);
+    k_sgemm<<<grid, 256, 0, st>>>(g);
+}
+
+// -----------------------------------------------------------------------------------------
+// ChannelNorm + ReLU in place on rows of 256 (encoder_components.py:62-70, 99-103).
+// LayerNorm(256) (+ optional GELU) (modules.py:242-243, 268; encoder_components.py:408-428).
+// One warp per row; lane owns columns {4*lane.., 128+4*lane..}.
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row8(const float* p, int lane, float v[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p + lane * 4);
+    const float4 b = *reinterpret_cast<const float4*>(p + 128 + lane * 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store_row8(float* p, int lane, const float v[8]) {
+    *reinterpret_cast<float4*>(p + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+// normalise v[8] (one 256-wide row spread over a warp); denom = 255 (unbiased) or 256 (biased)
+__device__ __forceinline__ void warp_norm8(float v[8], float denom_inv, const float* w, const float* b, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / 256.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float d = v[i] - mean;
+        q = fmaf(d, d, q);
+    }
+    const float var = warp_sum(q) * denom_inv;
+    const float rstd = 1.0f / sqrtf(var + kEps);
+    float ww[8], bb[8];
+    load_row8(w, lane, ww);
+    load_row8(b, lane, bb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * ww[i] + bb[i];
+}
+
+__global__ void __launch_bounds__(256) k_cn_relu(float* X, RowMap map, int M, const float* __restrict__ w,
+                                                 const float* __restrict__ b) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    float* p = X + rowmap_off(map, row);
+    float v[8];
+    load_row8(p, lane, v);
+    warp_norm8(v, 1.0f / 255.0f, w, b, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    store_row8(p, lane, v);
+}
+void launch_cn_relu(float* X, RowMap map, int M, const float* w, const float* b, cudaStream_t st) {
+    k_cn_relu<<<(M + 7) / 8, 256, 0, st>>>(X, map, M, w, b);
+}
+
+__global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ X, RowMap xmap, float* __restrict__ Y,
+                                                   RowMap ymap, int M, const float* __restrict__ w,
+                                                   const float* __restrict__ b, int gelu) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    float v[8];
+    load_row8(X + rowmap_off(xmap, row), lane, v);
+    warp_norm8(v, 1.0f / 256.0f, w, b, lane);
+    if (gelu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    }
+    store_row8(Y + rowmap_off(ymap, row), lane, v);
+}
+void launch_layernorm(const float* X, RowMap xmap, float* Y, RowMap ymap, int M, const float* w,
+                      const float* b, int gelu, cudaStream_t st) {
+    k_layernorm<<<(M + 7) / 8, 256, 0, st>>>(X, xmap, Y, ymap, M, w, b, gelu);
+}
+
+// -----------------------------------------------------------------------------------------
+// LSTM state staging and cell (encoder_components.py:120-123, 140-153; gate order i,f,g,o).
+// State arrays are [max_streams][2][256]; work arrays are [2B][256] in batch order.
+// -----------------------------------------------------------------------------------------
+__global__ void k_gather_state(const float* __restrict__ hS, const float* __restrict__ cS,
+                               const int* __restrict__ ids, float* hW, float* cW, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // float4 index over [2B][64]
+    if (i >= B * 2 * 64) return;
+    const int n = i / 64, q = i % 64;
+    const int b = n >> 1, ch = n & 1;
+    const size_t src = ((size_t)ids[b] * 2 + ch) * 64 + q;
+    reinterpret_cast<float4*>(hW)[i] = reinterpret_cast<const float4*>(hS)[src];
+    reinterpret_cast<float4*>(cW)[i] = reinterpret_cast<const float4*>(cS)[src];
+}
+void launch_gather_state(const float* hS, const float* cS, const int* ids, float* hW, float* cW, int B,
+                         cudaStream_t st) {
+    const int n = B * 2 * 64;
+    k_gather_state<<<(n + 255) / 256, 256, 0, st>>>(hS, cS, ids, hW, cW, B);
+}
+__global__ void k_scatter_state(float* hS, float* cS, const int* __restrict__ ids, const float* __restrict__ hW,
+                                const float* __restrict__ cW, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 2 * 64) return;
+    const int n = i / 64, q = i % 64;
+    const int b = n >> 1, ch = n & 1;
+    const size_t dst = ((size_t)ids[b] * 2 + ch) * 64 + q;
+    reinterpret_cast<float4*>(hS)[dst] = reinterpret_cast<const float4*>(hW)[i];
+    reinterpret_cast<float4*>(cS)[dst] = reinterpret_cast<const float4*>(cW)[i];
+}
+void launch_scatter_state(float* hS, float* cS, const int* ids, const float* hW, const float* cW, int B,
+                          cudaStream_t st) {
+    const int n = B * 2 * 64;
+    k_scatter_state<<<(n + 255) / 256, 256, 0, st>>>(hS, cS, ids, hW, cW, B);
+}
+
+// G [n_rows][1024] = W_ih x_t + b_ih + W_hh h + b_hh (already summed by the GEMMs)
+__global__ void k_lstm_cell(const float* __restrict__ G, float* hW, float* cW, float* __restrict__ Y, int n_rows,
+                            int n_steps, int step) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * kD) return;
+    const int n = i / kD, d = i % kD;
+    const float* g = G + (size_t)n * 4 * kD;
+    const float gi = g[d], gf = g[kD + d], gg = g[2 * kD + d], go = g[3 * kD + d];
+    const float c = sigmoidf_(gf) * cW[i] + sigmoidf_(gi) * tanhf(gg);
+    const float h = sigmoidf_(go) * tanhf(c);
+    cW[i] = c;
+    hW[i] = h;
+    Y[((size_t)n * n_steps + step) * kD + d] = h;
+}
+void launch_lstm_cell(const float* G, float* hW, float* cW, float* Y, int n_rows, int n_steps, int step,
+                      cudaStream_t st) {
+    const int n = n_rows * kD;
+    k_lstm_cell<<<(n + 255) / 256, 256, 0, st>>>(G, hW, cW, Y, n_rows, n_steps, step);
+}
+
+// -----------------------------------------------------------------------------------------
+// Downsample tail: LayerNorm + GELU, then append to the per-stream ring
+// (encoder_components.py:496-511; vap_main.py:274-280).  The frame counter is
+// advanced by the head kernel at the end of the step, so every kernel of a step
+// sees count = frames BEFORE this step.
+// ring layout: [max_streams][2][T][256]; slot of the new frame = count % T.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ln_gelu_ring(const float* __restrict__ X, int B, const float* __restrict__ w,
+                                                      const float* __restrict__ b, float* ring,
+                                                      const int* __restrict__ count, const int* __restrict__ ids,
+                                                      int T, float* e_out) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= 2 * B) return;
+    const int lane = threadIdx.x & 31;
+    float v[8];
+    load_row8(X + (size_t)n * kD, lane, v);
+    warp_norm8(v, 1.0f / 256.0f, w, b, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    const int id = ids[n >> 1], ch = n & 1;
+    const int slot = count[id] % T;
+    store_row8(ring + (((size_t)id * 2 + ch) * T + slot) * kD, lane, v);
+    if (e_out) store_row8(e_out + (size_t)n * kD, lane, v);
+}
+void launch_ln_gelu_ring(const float* X, int B, const float* w, const float* b, float* ring, const int* count,
+                         const int* ids, int T, float* e_out, cudaStream_t st) {
+    k_ln_gelu_ring<<<(2 * B + 7) / 8, 256, 0, st>>>(X, B, w, b, ring, count, ids, T, e_out);
+}
+
+// X[(n*T + j)] = ring row of logical position j (oldest first) for j < t, zero rows above.
+// (torch.cat of the context list, vap_main.py:282-283.)
+__global__ void __launch_bounds__(64) k_gather_ring(const float* __restrict__ ring, const int* __restrict__ count,
+                                                    const int* __restrict__ ids, float* __restrict__ X,
+                                                    int* __restrict__ tvalid, int B, int T) {
+    const int j = blockIdx.x, n = blockIdx.y;
+    const int b = n >> 1, ch = n & 1;
+    const int id = ids[b];
+    const int cnt = count[id] + 1;                 // frames including the one appended this step
+    const int t = cnt < T ? cnt : T;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < t) {
+        const int slot = (cnt - t + j) % T;
+        v = reinterpret_cast<const float4*>(ring + (((size_t)id * 2 + ch) * T + slot) * kD)[threadIdx.x];
+    }
+    reinterpret_cast<float4*>(X + ((size_t)n * T + j) * kD)[threadIdx.x] = v;
+    if (j == 0 && ch == 0 && threadIdx.x == 0) tvalid[b] = t;
+}
+void launch_gather_ring(const float* ring, const int* count, const int* ids, float* X, int* tvalid, int B, int T,
+                        cudaStream_t st) {
+    dim3 grid(T, 2 * B);
+    k_gather_ring<<<grid, 64, 0, st>>>(ring, count, ids, X, tvalid, B, T);
+}
+
+// -----------------------------------------------------------------------------------------
+// Causal ALiBi attention for one (sequence, head) per CTA (modules.py:82-110, 170-212):
+//   S[i][j] = (q_i . k_j) / 16 + m_h * j   (j <= i),  P = softmax_j S,  O = P V
+// scale = 1/sqrt(dim) = 1/16 (modules.py:52).  T <= 128.
+// -----------------------------------------------------------------------------------------
+constexpr int kAttnWarps = 8;
+
+__global__ void __launch_bounds__(kAttnWarps * 32) k_attention(AttnArgs a) {
+    extern __shared__ float smem[];
+    const int T = a.T;
+    float* sK = smem;                       // [T][65]
+    float* sV = sK + T * 65;                // [T][64]
+    float* sQ = sV + T * 64;                // [warps][64]
+    float* sP = sQ + kAttnWarps * 64;       // [warps][128]
+    const int n = blockIdx.x, h = blockIdx.y;
+    const int t = a.tvalid[n >> 1];
+    const int kvn = a.sibling ? (n ^ 1) : n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < t * 16; i += blockDim.x) {
+        const int j = i >> 4, q = (i & 15) * 4;
+        const size_t r = (size_t)kvn * T + j;
+        const float4 kk = *reinterpret_cast<const float4*>(a.K + r * a.ldk + h * 64 + q);
+        const float4 vv = *reinterpret_cast<const float4*>(a.V + r * a.ldv + h * 64 + q);
+        float* dk = sK + j * 65 + q;
+        dk[0] = kk.x; dk[1] = kk.y; dk[2] = kk.z; dk[3] = kk.w;
+        *reinterpret_cast<float4*>(sV + j * 64 + q) = vv;
+    }
+    __syncthreads();
+    const float slope = a.slopes[h];
+    float* q = sQ + warp * 64;
+    float* p = sP + warp * 128;
+    for (int i = warp; i < T; i += kAttnWarps) {
+        float* orow = a.O + ((size_t)n * T + i) * a.ldo + h * 64;
+        if (i >= t) {                       // rows beyond the valid window: defined zeros
+            orow[lane] = 0.f;
+            orow[lane + 32] = 0.f;
+            continue;
+        }
+        const float* qrow = a.Q + ((size_t)n * T + i) * a.ldq + h * 64;
+        q[lane] = qrow[lane];
+        q[lane + 32] = qrow[lane + 32];
+        __syncwarp();
+        float s[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = lane + 32 * jj;
+            s[jj] = -INFINITY;
+            if (j <= i) {
+                const float* kr = sK + j * 65;
+                float acc = 0.f;
+#pragma unroll 16
+                for (int d = 0; d < 64; ++d) acc = fmaf(q[d], kr[d], acc);
+                s[jj] = acc * 0.0625f + slope * (float)j;
+            }
+            mx = fmaxf(mx, s[jj]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = lane + 32 * jj;
+            const float e = (j <= i) ? expf(s[jj] - mx) : 0.f;
+            s[jj] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = lane + 32 * jj;
+            if (j < 128) p[j] = s[jj] * inv;
+        }
+        __syncwarp();
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j <= i; ++j) {
+            const float pj = p[j];
+            o0 = fmaf(pj, sV[j * 64 + lane], o0);
+            o1 = fmaf(pj, sV[j * 64 + lane + 32], o1);
+        }
+        orow[lane] = o0;
+        orow[lane + 32] = o1;
+        __syncwarp();
+    }
+}
+void launch_attention(const AttnArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)(a.T * 65 + a.T * 64 + kAttnWarps * 64 + kAttnWarps * 128) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    dim3 grid(a.n_seq, kHeads);
+    k_attention<<<grid, kAttnWarps * 32, smem, st>>>(a);
+}
+
+// -----------------------------------------------------------------------------------------
+// vad = sigmoid(va_classifier(ar_channel output at the last valid frame))
+// (vap_main.py:292-293, 313-314).  One warp per (stream, channel).
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vad(const float* __restrict__ X, const int* __restrict__ tvalid,
+                                             const float* __restrict__ w, const float* __restrict__ b,
+                                             float* __restrict__ out, int B, int T) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= 2 * B) return;
+    const int lane = threadIdx.x & 31;
+    const int t = tvalid[n >> 1];
+    float v[8], ww[8];
+    load_row8(X + ((size_t)n * T + (t - 1)) * kD, lane, v);
+    load_row8(w, lane, ww);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(v[i], ww[i], s);
+    s = warp_sum(s) + b[0];
+    if (lane == 0) out[(n >> 1) * 6 + 4 + (n & 1)] = sigmoidf_(s);
+}
+void launch_vad(const float* X, const int* tvalid, const float* w, const float* b, float* out, int B, int T,
+                cudaStream_t st) {
+    k_vad<<<(2 * B + 7) / 8, 256, 0, st>>>(X, tvalid, w, b, out, B, T);
+}
+
+// -----------------------------------------------------------------------------------------
+// Head: Combinator (modules.py:461-464) on the last valid frame, vap_head / bc_head,
+// softmax, codebook aggregation and normalisation (vap_main.py:290-317;
+// objective.py:93-110, 186-206; vap_bc_main.py:272-277).  One CTA per stream.
+// Also advances the stream's frame counter (last kernel of the step).
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_dot256(const float* __restrict__ wrow, const float* sx, int lane) {
+    float ww[8];
+    load_row8(wrow, lane, ww);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s = fmaf(ww[i], sx[lane * 4 + i], s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s = fmaf(ww[4 + i], sx[128 + lane * 4 + i], s);
+    return warp_sum(s);
+}
+
+__global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+    __shared__ float sx[2][kD];
+    __shared__ float sy[2][kD];
+    __shared__ float sh[kD];
+    __shared__ float sl[kD];
+    __shared__ float red[5][8];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = a.tvalid[b];
+    sx[0][tid] = a.X[((size_t)(2 * b) * a.T + (t - 1)) * kD + tid];
+    sx[1][tid] = a.X[((size_t)(2 * b + 1) * a.T + (t - 1)) * kD + tid];
+    __syncthreads();
+    for (int o = warp; o < kD; o += 8) {
+        const float ya = warp_dot256(a.Wa + (size_t)o * kD, sx[0], lane);
+        const float yb = warp_dot256(a.Wb + (size_t)o * kD, sx[1], lane);
+        if (lane == 0) {
+            sy[0][o] = ya;
+            sy[1][o] = yb;
+        }
+    }
+    __syncthreads();
+    if (warp < 2) {                         // one LayerNorm + GELU per channel, shared affine
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i] = sy[warp][lane * 4 + i];
+            v[4 + i] = sy[warp][128 + lane * 4 + i];
+        }
+        warp_norm8(v, 1.0f / 256.0f, a.lnw, a.lnb, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            sy[warp][lane * 4 + i] = gelu_erf(v[i]);
+            sy[warp][128 + lane * 4 + i] = gelu_erf(v[4 + i]);
+        }
+    }
+    __syncthreads();
+    sh[tid] = sy[0][tid] + sy[1][tid];
+    if (a.comb_tap) a.comb_tap[(size_t)b * kD + tid] = sh[tid];
+    __syncthreads();
+    for (int o = warp; o < a.n_out; o += 8) {
+        const float y = warp_dot256(a.Wh + (size_t)o * kD, sh, lane) + a.bh[o];
+        if (lane == 0) sl[o] = y;
+    }
+    __syncthreads();
+    if (a.logits_tap && tid < a.n_out) a.logits_tap[(size_t)b * kD + tid] = sl[tid];
+    float* out = a.out + (size_t)b * 6;
+    if (a.head_kind == 0) {
+        // softmax over 256 classes, then p[s] = sum_c pi_c * (#active bins of speaker s in the range)
+        float lg = sl[tid];
+        float mx = warp_max(lg);
+        if (lane == 0) red[0][warp] = mx;
+        __syncthreads();
+        mx = red[0][0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[0][i]);
+        __syncthreads();
+        const float e = expf(lg - mx);
+        const int c = tid;
+        float vals[5];
+        vals[0] = e;
+        vals[1] = e * (float)(((c >> 0) & 1) + ((c >> 1) & 1));     // now,    speaker 0: bins 0,1
+        vals[2] = e * (float)(((c >> 4) & 1) + ((c >> 5) & 1));     // now,    speaker 1
+        vals[3] = e * (float)(((c >> 2) & 1) + ((c >> 3) & 1));     // future, speaker 0: bins 2,3
+        vals[4] = e * (float)(((c >> 6) & 1) + ((c >> 7) & 1));     // future, speaker 1
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float s = warp_sum(vals[k]);
+            if (lane == 0) red[k][warp] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float tot[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s += red[k][i];
+                tot[k] = s;
+            }
+            const float inv = 1.0f / tot[0];
+            const float n0 = tot[1] * inv, n1 = tot[2] * inv, f0 = tot[3] * inv, f1 = tot[4] * inv;
+            const float dn = n0 + n1 + kEps, df = f0 + f1 + kEps;         // objective.py:205
+            out[0] = n0 / dn;
+            out[1] = n1 / dn;
+            out[2] = f0 / df;
+            out[3] = f1 / df;
+            // out[4], out[5] (vad) were written by k_vad after the ar_channel layer
+        }
+    } else {
+        if (tid == 0) {
+            const float l0 = sl[0], l1 = sl[1], l2 = sl[2];
+            const float mx = fmaxf(l0, fmaxf(l1, l2));
+            const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+            const float inv = 1.0f / (e0 + e1 + e2);
+            out[0] = e1 * inv;          // p_bc_react = softmax[..., 1]   vap_bc_main.py:276
+            out[1] = e2 * inv;          // p_bc_emo   = softmax[..., 2]   vap_bc_main.py:277
+            out[2] = 0.f; out[3] = 0.f; out[4] = 0.f; out[5] = 0.f;
+        }
+    }
+    if (tid == 0) a.count[a.ids[b]] += 1;
+}
+void launch_head(const HeadArgs& a, cudaStream_t st) { k_head<<<a.B, 256, 0, st>>>(a); }
+
+}  // namespace vapb

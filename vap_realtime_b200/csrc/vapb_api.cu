@@ -1,0 +1,926 @@
+// libvapb200: context, weight loading, step orchestration and the C ABI
+// declared in include/vapb200.h.
+#include "../../include/vapb200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace vapb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostTensor {
+    const float* data;
+    int ndim;
+    uint32_t dims[4];
+    size_t numel;
+};
+
+struct ConvLayer {           // conv1..conv4 as GEMMs over channels-last activations
+    int k, s, p, Lin, Lout;
+    float* W;                // [256][k*256], K index = tap*256 + cin
+    float* b;
+    float* cnw;
+    float* cnb;
+    TcWeight tc;             // bf16 hi/lo planes of W for the tcgen05 path
+};
+
+struct AttnWeights {
+    float* Wqkv;             // self: [768][256] = [Wq; Wk; Wv]
+    float* Wproj;            // [256][256]
+    float* slopes;           // [4]
+    TcWeight tc_qkv, tc_proj;
+};
+struct LayerWeights {
+    float *ln_sa_w, *ln_sa_b, *ln_ff_w, *ln_ff_b;
+    AttnWeights sa;
+    float* W1;               // [768][256]
+    float* W2;               // [256][768]
+    TcWeight tc_w1, tc_w2;
+    // cross attention (ar.layers.*) only
+    bool cross;
+    float *ln_src_w, *ln_src_b;
+    float* Wq_c;             // [256][256]
+    float* Wkv_c;            // [512][256] = [Wk; Wv]
+    float* Wproj_c;
+    float* slopes_c;
+    TcWeight tc_q_c, tc_kv_c, tc_proj_c;
+};
+
+struct GraphEntry {
+    int B;
+    const float* audio;
+    float* out;
+    cudaGraphExec_t exec;
+    int launches;
+};
+
+}  // namespace
+
+struct vapb_ctx {
+    int device = 0;
+    int frame_hz = 20, T = 50, max_streams = 0, max_batch = 0, head_kind = 0;
+    int S = 1120;                    // samples per chunk
+    int L[5] = {0, 0, 0, 0, 0};      // conv output lengths
+    int n_lstm = 5;                  // frames fed to the LSTM (= downsample taps)
+    std::string err;
+
+    std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in destroy
+
+    // weights
+    float *w0 = nullptr, *b0 = nullptr, *cn0w = nullptr, *cn0b = nullptr;
+    ConvLayer conv[4];
+    float *Wih = nullptr, *Whh = nullptr, *b_lstm = nullptr;
+    float *Wds = nullptr, *bds = nullptr, *ds_lnw = nullptr, *ds_lnb = nullptr;
+    TcWeight tc_ds;
+    LayerWeights layers[4];          // [0] = ar_channel.layers.0, [1..3] = ar.layers.0..2
+    float *Wa = nullptr, *Wb = nullptr, *comb_lnw = nullptr, *comb_lnb = nullptr;
+    float *Wh = nullptr, *bh = nullptr;
+    int n_out = 256;
+    float *va_w = nullptr, *va_b = nullptr;
+
+    // per-stream state
+    float *hS = nullptr, *cS = nullptr, *ring = nullptr;
+    int* count = nullptr;
+
+    // per-step workspaces (sized for max_batch)
+    int* ids_dev = nullptr;
+    int* ids_pinned = nullptr;
+    int* tvalid = nullptr;
+    float* act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // channels-last, with halo rows
+    int halo[5] = {0, 0, 0, 0, 0};
+    float *hW = nullptr, *cW = nullptr, *Gx = nullptr, *Gt = nullptr, *Y = nullptr, *dsout = nullptr, *ebuf = nullptr;
+    float *X = nullptr, *Z = nullptr, *QKV = nullptr, *O = nullptr, *Hd = nullptr, *KVc = nullptr, *Qc = nullptr;
+    float* audio_stage = nullptr;    // device staging for vapb_step_host
+    float* out_stage = nullptr;
+    TcWorkspace tcws;                // bf16 hi/lo activation planes for the tcgen05 path
+
+    // taps
+    std::map<std::string, std::pair<float*, size_t>> taps;
+    float *tap_chan = nullptr, *tap_cross[3] = {nullptr, nullptr, nullptr}, *tap_comb = nullptr, *tap_logits = nullptr,
+          *tap_xin = nullptr;
+    int last_B = 0;
+
+    // options
+    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0;
+    std::vector<GraphEntry> graphs;
+    int launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+namespace {
+
+int fail(vapb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(c, call)                                                                                    \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail((c), VAPB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),       \
+                        __FILE__, __LINE__);                                                           \
+    } while (0)
+
+// ---- VAPW blob parsing (vap_realtime_b200/weights.py) ------------------------------------
+bool parse_blob(const void* blob, size_t nbytes, std::map<std::string, HostTensor>& out, std::string& err) {
+    const uint8_t* p = static_cast<const uint8_t*>(blob);
+    if (nbytes < 16 || memcmp(p, "VAPW0001", 8) != 0) {
+        err = "weight blob: bad magic";
+        return false;
+    }
+    uint32_t n, tb;
+    memcpy(&n, p + 8, 4);
+    memcpy(&tb, p + 12, 4);
+    if (tb != n * 96u || 16 + (size_t)tb > nbytes) {
+        err = "weight blob: corrupt table";
+        return false;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t* e = p + 16 + (size_t)i * 96;
+        char name[65];
+        memcpy(name, e, 64);
+        name[64] = 0;
+        HostTensor t;
+        uint32_t ndim;
+        memcpy(&ndim, e + 64, 4);
+        memcpy(t.dims, e + 68, 16);
+        uint64_t off;
+        uint32_t nb;
+        memcpy(&off, e + 84, 8);
+        memcpy(&nb, e + 92, 4);
+        if (ndim > 4 || off + nb > nbytes || (off & 3)) {
+            err = std::string("weight blob: bad entry ") + name;
+            return false;
+        }
+        t.ndim = (int)ndim;
+        t.numel = nb / 4;
+        t.data = reinterpret_cast<const float*>(p + off);
+        out[name] = t;
+    }
+    return true;
+}
+
+struct Loader {
+    vapb_ctx* c;
+    std::map<std::string, HostTensor> t;
+    std::string err;
+    bool ok = true;
+
+    const HostTensor* get(const std::string& name, std::initializer_list<uint32_t> shape) {
+        auto it = t.find(name);
+        if (it == t.end()) {
+            if (ok) err = "missing tensor " + name;
+            ok = false;
+            return nullptr;
+        }
+        const HostTensor& h = it->second;
+        size_t numel = 1;
+        int i = 0;
+        bool match = (int)shape.size() == h.ndim;
+        for (uint32_t d : shape) {
+            if (match && h.dims[i] != d) match = false;
+            numel *= d;
+            ++i;
+        }
+        if (!match || numel != h.numel) {
+            if (ok) err = "wrong shape for " + name;
+            ok = false;
+            return nullptr;
+        }
+        return &h;
+    }
+    float* upload(const std::vector<float>& v) {
+        float* d = nullptr;
+        if (cudaMalloc(&d, std::max<size_t>(v.size(), 4) * sizeof(float)) != cudaSuccess) {
+            if (ok) err = "cudaMalloc failed (weights)";
+            ok = false;
+            return nullptr;
+        }
+        c->allocs.push_back(d);
+        cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+        return d;
+    }
+    float* up(const std::string& name, std::initializer_list<uint32_t> shape) {
+        const HostTensor* h = get(name, shape);
+        if (!h) return nullptr;
+        return upload(std::vector<float>(h->data, h->data + h->numel));
+    }
+    // Conv1d weight [Cout][Cin][k] -> GEMM weight [Cout][k*Cin] (K index = tap*Cin + cin), matching
+    // the channels-last activation rows (tap-major K).
+    std::vector<float> conv_as_gemm(const std::string& name, uint32_t k) {
+        const HostTensor* h = get(name, {256u, 256u, k});
+        std::vector<float> v;
+        if (!h) return v;
+        v.resize((size_t)256 * k * 256);
+        for (uint32_t n = 0; n < 256; ++n)
+            for (uint32_t ci = 0; ci < 256; ++ci)
+                for (uint32_t tap = 0; tap < k; ++tap)
+                    v[(size_t)n * k * 256 + tap * 256 + ci] = h->data[((size_t)n * 256 + ci) * k + tap];
+        return v;
+    }
+    std::vector<float> concat(std::initializer_list<const HostTensor*> parts) {
+        std::vector<float> v;
+        for (const HostTensor* h : parts)
+            if (h) v.insert(v.end(), h->data, h->data + h->numel);
+        return v;
+    }
+};
+
+template <typename Tp>
+int dalloc(vapb_ctx* c, Tp** p, size_t n, bool zero = true) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(Tp));
+    if (e != cudaSuccess) return fail(c, VAPB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(Tp), cudaGetErrorString(e));
+    c->allocs.push_back(d);
+    if (zero) cudaMemset(d, 0, std::max<size_t>(n, 1) * sizeof(Tp));
+    *p = static_cast<Tp*>(d);
+    return 0;
+}
+
+RowMap act_map(const vapb_ctx* c, int layer) {      // logical row = chunk*L + position
+    RowMap m;
+    m.rpc = c->L[layer];
+    m.chunk_stride = (long long)(c->L[layer] + 2 * c->halo[layer]) * kD;
+    m.row_stride = kD;
+    m.offset = (long long)c->halo[layer] * kD;
+    return m;
+}
+
+int load_layer(Loader& ld, LayerWeights& lw, const std::string& p, bool cross) {
+    lw.cross = cross;
+    lw.ln_sa_w = ld.up(p + "ln_self_attn.weight", {256});
+    lw.ln_sa_b = ld.up(p + "ln_self_attn.bias", {256});
+    lw.ln_ff_w = ld.up(p + "ln_ffnetwork.weight", {256});
+    lw.ln_ff_b = ld.up(p + "ln_ffnetwork.bias", {256});
+    lw.sa.Wqkv = ld.upload(ld.concat({ld.get(p + "mha.query.weight", {256, 256}), ld.get(p + "mha.key.weight", {256, 256}),
+                                      ld.get(p + "mha.value.weight", {256, 256})}));
+    lw.sa.Wproj = ld.up(p + "mha.proj.weight", {256, 256});
+    lw.sa.slopes = ld.up(p + "mha.m", {4});
+    lw.W1 = ld.up(p + "ffnetwork.0.weight", {768, 256});
+    lw.W2 = ld.up(p + "ffnetwork.3.weight", {256, 768});
+    if (cross) {
+        lw.ln_src_w = ld.up(p + "ln_src_attn.weight", {256});
+        lw.ln_src_b = ld.up(p + "ln_src_attn.bias", {256});
+        lw.Wq_c = ld.up(p + "mha_cross.query.weight", {256, 256});
+        lw.Wkv_c = ld.upload(ld.concat({ld.get(p + "mha_cross.key.weight", {256, 256}),
+                                        ld.get(p + "mha_cross.value.weight", {256, 256})}));
+        lw.Wproj_c = ld.up(p + "mha_cross.proj.weight", {256, 256});
+        lw.slopes_c = ld.up(p + "mha_cross.m", {4});
+    }
+    return 0;
+}
+
+// ---- the step ---------------------------------------------------------------------------
+struct Step {
+    vapb_ctx* c;
+    cudaStream_t st;
+    int B;
+    const float* audio;
+    float* out;
+    int n = 0;      // launches
+    std::vector<std::pair<const char*, cudaEvent_t>>* prof = nullptr;   // per-launch events (vapb_profile_step)
+};
+
+// bookkeeping after every kernel launch: count it and, when profiling, drop an event behind it
+void mark(Step& s, const char* tag, int launches = 1) {
+    s.n += launches;
+    if (s.prof) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s.st);
+        s.prof->push_back({tag, e});
+    }
+}
+
+// C = act(A W^T + bias) + R through the selected GEMM engine.
+void gemm(Step& s, const char* tag, const float* A, RowMap amap, const float* W, const TcWeight* tcw, const float* bias,
+          const float* R, RowMap rmap, float* C, RowMap cmap, int M, int N, int K, int act) {
+    GemmArgs g;
+    g.A = A; g.amap = amap; g.W = W; g.bias = bias; g.R = R; g.rmap = rmap; g.C = C; g.cmap = cmap;
+    g.M = M; g.N = N; g.K = K; g.act = act;
+    if (s.c->opt_gemm == 1 && tcw && tcw->hi) {
+        mark(s, tag, launch_gemm_tc(g, *tcw, s.c->tcws, s.st));
+    } else {
+        launch_sgemm(g, s.st);
+        mark(s, tag);
+    }
+}
+
+void tap_copy(Step& s, float* dst, const float* src, size_t n) {
+    if (s.c->opt_keep_taps && dst) cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s.st);
+}
+
+void attention(Step& s, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O,
+               const float* slopes, int sibling) {
+    AttnArgs a;
+    a.Q = Q; a.ldq = ldq; a.K = K; a.ldk = ldk; a.V = V; a.ldv = ldv; a.O = O; a.ldo = kD;
+    a.tvalid = s.c->tvalid; a.slopes = slopes; a.n_seq = 2 * s.B; a.T = s.c->T; a.sibling = sibling;
+    launch_attention(a, s.st);
+    mark(s, sibling ? "attn_cross" : "attn_self");
+}
+
+void transformer_layer(Step& s, const LayerWeights& lw) {
+    vapb_ctx* c = s.c;
+    const int R = 2 * s.B * c->T;
+    const RowMap pd = plain_map(kD), pf = plain_map(kFF), p3 = plain_map(3 * kD), p2 = plain_map(2 * kD);
+    if (lw.cross) {
+        // K/V of the cross attention come from the RAW layer input of the sibling channel
+        // (modules.py:276-283), so project it before X is updated in place.
+        gemm(s, "gemm_kv_cross", c->X, pd, lw.Wkv_c, &lw.tc_kv_c, nullptr, nullptr, pd, c->KVc, p2, R, 2 * kD, kD, 0);
+    }
+    // self attention block (modules.py:268-272)
+    launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_sa_w, lw.ln_sa_b, 0, s.st); mark(s, "layernorm");
+    gemm(s, "gemm_qkv", c->Z, pd, lw.sa.Wqkv, &lw.sa.tc_qkv, nullptr, nullptr, pd, c->QKV, p3, R, 3 * kD, kD, 0);
+    attention(s, c->QKV, 3 * kD, c->QKV + kD, 3 * kD, c->QKV + 2 * kD, 3 * kD, c->O, lw.sa.slopes, 0);
+    gemm(s, "gemm_proj", c->O, pd, lw.sa.Wproj, &lw.sa.tc_proj, nullptr, c->X, pd, c->X, pd, R, kD, kD, 0);
+    if (lw.cross) {
+        launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_src_w, lw.ln_src_b, 0, s.st); mark(s, "layernorm");
+        gemm(s, "gemm_q_cross", c->Z, pd, lw.Wq_c, &lw.tc_q_c, nullptr, nullptr, pd, c->Qc, pd, R, kD, kD, 0);
+        attention(s, c->Qc, kD, c->KVc, 2 * kD, c->KVc + kD, 2 * kD, c->O, lw.slopes_c, 1);
+        gemm(s, "gemm_proj", c->O, pd, lw.Wproj_c, &lw.tc_proj_c, nullptr, c->X, pd, c->X, pd, R, kD, kD, 0);
+    }
+    // feed forward (modules.py:9-21, 285): Linear(256,768) -> GELU -> Linear(768,256), no biases
+    launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_ff_w, lw.ln_ff_b, 0, s.st); mark(s, "layernorm");
+    gemm(s, "gemm_ffn1", c->Z, pd, lw.W1, &lw.tc_w1, nullptr, nullptr, pd, c->Hd, pf, R, kFF, kD, 1);
+    gemm(s, "gemm_ffn2", c->Hd, pf, lw.W2, &lw.tc_w2, nullptr, c->X, pd, c->X, pd, R, kD, kFF, 0);
+}
+
+void enqueue_step(Step& s) {
+    vapb_ctx* c = s.c;
+    const int B = s.B, NC = 2 * B, T = c->T;
+    cudaStream_t st = s.st;
+
+    // ---- CPC encoder on the newest chunk (encoder.py:58-80)
+    launch_conv0(s.audio, NC, c->S, c->L[0], c->w0, c->b0, c->cn0w, c->cn0b, c->act[0], act_map(c, 0), st); mark(s, "conv0_cn_relu");
+    for (int i = 0; i < 4; ++i) {
+        const ConvLayer& cv = c->conv[i];
+        // im2col-free: output row p of a chunk reads k*256 contiguous floats starting at input
+        // row (s*p - pad); the zero halo rows of the input buffer are the conv padding.
+        RowMap am;
+        am.rpc = cv.Lout;
+        am.chunk_stride = (long long)(cv.Lin + 2 * c->halo[i]) * kD;
+        am.row_stride = (long long)cv.s * kD;
+        am.offset = (long long)(c->halo[i] - cv.p) * kD;
+        const RowMap cm = act_map(c, i + 1);
+        gemm(s, i == 0 ? "gemm_conv1" : "gemm_conv2_4", c->act[i], am, cv.W, &cv.tc, cv.b, nullptr, cm, c->act[i + 1], cm, NC * cv.Lout, kD, cv.k * kD, 0);
+        launch_cn_relu(c->act[i + 1], cm, NC * cv.Lout, cv.cnw, cv.cnb, st); mark(s, "cn_relu");
+    }
+    // ---- LSTM over the inner frames z[:, 1:-1] with persistent (h, c) (encoder.py:76-77)
+    launch_gather_state(c->hS, c->cS, c->ids_dev, c->hW, c->cW, B, st); mark(s, "lstm_state");
+    {
+        RowMap am;
+        am.rpc = c->n_lstm;
+        am.chunk_stride = (long long)(c->L[4] + 2 * c->halo[4]) * kD;
+        am.row_stride = kD;
+        am.offset = (long long)(c->halo[4] + 1) * kD;
+        const RowMap g4 = plain_map(4 * kD);
+        gemm(s, "gemm_lstm_x", c->act[4], am, c->Wih, nullptr, c->b_lstm, nullptr, g4, c->Gx, g4, NC * c->n_lstm, 4 * kD, kD, 0);
+        for (int t = 0; t < c->n_lstm; ++t) {
+            RowMap rm;
+            rm.rpc = 1;
+            rm.chunk_stride = (long long)c->n_lstm * 4 * kD;
+            rm.row_stride = 0;
+            rm.offset = (long long)t * 4 * kD;
+            gemm(s, "gemm_lstm_h", c->hW, plain_map(kD), c->Whh, nullptr, nullptr, c->Gx, rm, c->Gt, g4, NC, 4 * kD, kD, 0);
+            launch_lstm_cell(c->Gt, c->hW, c->cW, c->Y, NC, c->n_lstm, t, st); mark(s, "lstm_cell");
+        }
+    }
+    launch_scatter_state(c->hS, c->cS, c->ids_dev, c->hW, c->cW, B, st); mark(s, "lstm_state");
+    // ---- downsample conv over exactly n_lstm frames + LayerNorm + GELU -> ring
+    {
+        const int Kd = c->n_lstm * kD;
+        gemm(s, "gemm_downsample", c->Y, plain_map(Kd), c->Wds, &c->tc_ds, c->bds, nullptr, plain_map(kD), c->dsout, plain_map(kD), NC, kD, Kd, 0);
+        launch_ln_gelu_ring(c->dsout, B, c->ds_lnw, c->ds_lnb, c->ring, c->count, c->ids_dev, T, c->ebuf, st); mark(s, "ln_gelu_ring");
+    }
+    // ---- window of the last T embeddings, oldest first (vap_main.py:274-283)
+    launch_gather_ring(c->ring, c->count, c->ids_dev, c->X, c->tvalid, B, T, st); mark(s, "gather_ring");
+    const size_t RX = (size_t)NC * T * kD;
+    tap_copy(s, c->tap_xin, c->X, RX);
+    // ---- ar_channel: one TransformerLayer per channel, shared weights (vap_main.py:285-286)
+    transformer_layer(s, c->layers[0]);
+    tap_copy(s, c->tap_chan, c->X, RX);
+    if (c->head_kind == VAPB_HEAD_VAP) {
+        launch_vad(c->X, c->tvalid, c->va_w, c->va_b, s.out, B, T, st); mark(s, "vad");
+    }
+    // ---- ar: three TransformerStereoLayers (modules.py:289-300, 395-423)
+    for (int li = 0; li < 3; ++li) {
+        transformer_layer(s, c->layers[1 + li]);
+        tap_copy(s, c->tap_cross[li], c->X, RX);
+    }
+    // ---- combinator + projection head + aggregation; advances the frame counters
+    HeadArgs h;
+    h.X = c->X; h.tvalid = c->tvalid; h.Wa = c->Wa; h.Wb = c->Wb; h.lnw = c->comb_lnw; h.lnb = c->comb_lnb;
+    h.Wh = c->Wh; h.bh = c->bh; h.n_out = c->n_out; h.out = s.out;
+    h.comb_tap = c->opt_keep_taps ? c->tap_comb : nullptr;
+    h.logits_tap = c->opt_keep_taps ? c->tap_logits : nullptr;
+    h.count = c->count; h.ids = c->ids_dev; h.B = B; h.T = T; h.head_kind = c->head_kind;
+    launch_head(h, st); mark(s, "head");
+}
+
+int check_ids(vapb_ctx* c, const int* ids, int B) {
+    if (B <= 0 || B > c->max_batch) return fail(c, VAPB_EINVAL, "B=%d outside 1..%d", B, c->max_batch);
+    if (!ids) return fail(c, VAPB_EINVAL, "stream_ids is NULL");
+    std::vector<int> v(ids, ids + B);
+    std::sort(v.begin(), v.end());
+    if (v.front() < 0 || v.back() >= c->max_streams) return fail(c, VAPB_EINVAL, "stream id outside 0..%d", c->max_streams - 1);
+    for (int i = 1; i < B; ++i)
+        if (v[i] == v[i - 1]) return fail(c, VAPB_EINVAL, "duplicate stream id %d in one batch", v[i]);
+    return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* vapb_version(void) { return "vapb200 0.1 sm_100a"; }
+
+const char* vapb_last_error(vapb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_frames, int max_streams,
+                int max_batch, int head_kind, int device, vapb_handle* out) {
+    if (!out) return fail(nullptr, VAPB_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!weights_blob) return fail(nullptr, VAPB_EINVAL, "weights_blob is NULL");
+    if (frame_hz != 20 && frame_hz != 10 && frame_hz != 5)
+        return fail(nullptr, VAPB_EUNSUPPORTED, "frame_hz %d not in {20,10,5}", frame_hz);
+    if (ctx_frames < 1 || ctx_frames > kMaxT)
+        return fail(nullptr, VAPB_EUNSUPPORTED, "ctx_frames %d outside 1..%d", ctx_frames, kMaxT);
+    if (max_streams < 1 || max_batch < 1 || max_batch > max_streams)
+        return fail(nullptr, VAPB_EINVAL, "need 1 <= max_batch <= max_streams");
+    if (head_kind != VAPB_HEAD_VAP && head_kind != VAPB_HEAD_BC)
+        return fail(nullptr, VAPB_EINVAL, "head_kind %d unknown", head_kind);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, VAPB_ECUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, VAPB_EINVAL, "device %d outside 0..%d", device, ndev - 1);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, VAPB_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, VAPB_EUNSUPPORTED, "device %d is sm_%d%d; libvapb200 is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, VAPB_ECUDA, "cudaSetDevice failed");
+
+    vapb_ctx* c = new vapb_ctx();
+    c->device = device; c->frame_hz = frame_hz; c->T = ctx_frames; c->max_streams = max_streams;
+    c->max_batch = max_batch; c->head_kind = head_kind;
+    c->S = 16000 / frame_hz + kPadSamples;
+    const int ck[5] = {10, 8, 4, 4, 4}, cs[5] = {5, 4, 2, 2, 2}, cp[5] = {3, 2, 1, 1, 1};
+    int len = c->S;
+    for (int i = 0; i < 5; ++i) {
+        len = (len + 2 * cp[i] - ck[i]) / cs[i] + 1;
+        c->L[i] = len;
+    }
+    c->n_lstm = c->L[4] - 2;
+    for (int i = 0; i < 4; ++i) c->halo[i] = cp[i + 1];   // halo rows of act[i] = padding of the conv that reads it
+    c->halo[4] = 0;
+
+#define FAIL_CREATE(code, ...)                       \
+    do {                                             \
+        int rc_ = fail(nullptr, code, __VA_ARGS__);  \
+        vapb_destroy(c);                             \
+        return rc_;                                  \
+    } while (0)
+
+    Loader ld;
+    ld.c = c;
+    if (!parse_blob(weights_blob, nbytes, ld.t, ld.err)) FAIL_CREATE(VAPB_EWEIGHTS, "%s", ld.err.c_str());
+    const std::string G = "encoder.encoder.gEncoder.", A = "encoder.encoder.gAR.baseNet.";
+    c->w0 = ld.up(G + "conv0.weight", {256, 1, 10});
+    c->b0 = ld.up(G + "conv0.bias", {256});
+    c->cn0w = ld.up(G + "batchNorm0.weight", {1, 256, 1});
+    c->cn0b = ld.up(G + "batchNorm0.bias", {1, 256, 1});
+    for (int i = 0; i < 4; ++i) {
+        ConvLayer& cv = c->conv[i];
+        cv.k = ck[i + 1]; cv.s = cs[i + 1]; cv.p = cp[i + 1]; cv.Lin = c->L[i]; cv.Lout = c->L[i + 1];
+        const std::string n = std::to_string(i + 1);
+        cv.W = ld.upload(ld.conv_as_gemm(G + "conv" + n + ".weight", (uint32_t)cv.k));
+        cv.b = ld.up(G + "conv" + n + ".bias", {256});
+        cv.cnw = ld.up(G + "batchNorm" + n + ".weight", {1, 256, 1});
+        cv.cnb = ld.up(G + "batchNorm" + n + ".bias", {1, 256, 1});
+    }
+    c->Wih = ld.up(A + "weight_ih_l0", {1024, 256});
+    c->Whh = ld.up(A + "weight_hh_l0", {1024, 256});
+    {
+        const HostTensor* bi = ld.get(A + "bias_ih_l0", {1024});
+        const HostTensor* bh = ld.get(A + "bias_hh_l0", {1024});
+        std::vector<float> b(1024, 0.f);
+        if (bi && bh)
+            for (int i = 0; i < 1024; ++i) b[i] = bi->data[i] + bh->data[i];
+        c->b_lstm = ld.upload(b);
+    }
+    {   // downsample Conv1d(256,256,k=n_lstm) as a GEMM over the n_lstm LSTM outputs (K = tap*256 + cin)
+        const uint32_t kd = (uint32_t)c->n_lstm;
+        c->Wds = ld.upload(ld.conv_as_gemm("encoder.downsample.1.weight", kd));
+        c->bds = ld.up("encoder.downsample.1.bias", {256});
+        c->ds_lnw = ld.up("encoder.downsample.2.ln.weight", {256});
+        c->ds_lnb = ld.up("encoder.downsample.2.ln.bias", {256});
+    }
+    load_layer(ld, c->layers[0], "ar_channel.layers.0.", false);
+    for (int i = 0; i < 3; ++i) load_layer(ld, c->layers[1 + i], "ar.layers." + std::to_string(i) + ".", true);
+    c->Wa = ld.up("ar.combinator.h0_a.weight", {256, 256});
+    c->Wb = ld.up("ar.combinator.h0_b.weight", {256, 256});
+    c->comb_lnw = ld.up("ar.combinator.ln.weight", {256});
+    c->comb_lnb = ld.up("ar.combinator.ln.bias", {256});
+    if (head_kind == VAPB_HEAD_VAP) {
+        c->n_out = 256;
+        c->Wh = ld.up("vap_head.weight", {256, 256});
+        c->bh = ld.up("vap_head.bias", {256});
+        c->va_w = ld.up("va_classifier.weight", {1, 256});
+        c->va_b = ld.up("va_classifier.bias", {1});
+    } else {
+        c->n_out = 3;
+        c->Wh = ld.up("bc_head.weight", {3, 256});
+        c->bh = ld.up("bc_head.bias", {3});
+    }
+    if (!ld.ok) FAIL_CREATE(VAPB_EWEIGHTS, "%s", ld.err.c_str());
+
+    // ---- state + workspaces
+    const size_t MS = (size_t)max_streams, MB = (size_t)max_batch, NC = 2 * MB, R = NC * c->T;
+    int rc = 0;
+#define DA(ptr, n) if (!rc) rc = dalloc(c, &(ptr), (n))
+    DA(c->hS, MS * 2 * kD);
+    DA(c->cS, MS * 2 * kD);
+    DA(c->ring, MS * 2 * c->T * kD);
+    DA(c->count, MS);
+    DA(c->ids_dev, MB);
+    DA(c->tvalid, MB);
+    for (int i = 0; i < 5; ++i) DA(c->act[i], NC * (size_t)(c->L[i] + 2 * c->halo[i]) * kD);
+    DA(c->hW, NC * kD);
+    DA(c->cW, NC * kD);
+    DA(c->Gx, NC * c->n_lstm * 4 * kD);
+    DA(c->Gt, NC * 4 * kD);
+    DA(c->Y, NC * c->n_lstm * kD);
+    DA(c->dsout, NC * kD);
+    DA(c->ebuf, NC * kD);
+    DA(c->X, R * kD);
+    DA(c->Z, R * kD);
+    DA(c->QKV, R * 3 * kD);
+    DA(c->O, R * kD);
+    DA(c->Hd, R * kFF);
+    DA(c->KVc, R * 2 * kD);
+    DA(c->Qc, R * kD);
+    DA(c->audio_stage, MB * 2 * c->S);
+    DA(c->out_stage, MB * 6);
+#undef DA
+    if (rc) {
+        g_create_error = c->err;
+        vapb_destroy(c);
+        return rc;
+    }
+    if (cudaMallocHost(reinterpret_cast<void**>(&c->ids_pinned), MB * sizeof(int)) != cudaSuccess)
+        FAIL_CREATE(VAPB_ENOMEM, "cudaMallocHost failed");
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+
+    // ---- tcgen05 operands: bf16 hi/lo planes of every tensor-core GEMM weight (+ workspaces)
+    {
+        std::string terr;
+        bool ok = true;
+        for (int i = 0; i < 4 && ok; ++i) ok = tc_prepare_weight(c->conv[i].W, kD, c->conv[i].k * kD, c->conv[i].tc, c->allocs, terr);
+        if (ok) ok = tc_prepare_weight(c->Wds, kD, c->n_lstm * kD, c->tc_ds, c->allocs, terr);
+        for (int l = 0; l < 4 && ok; ++l) {
+            LayerWeights& lw = c->layers[l];
+            ok = tc_prepare_weight(lw.sa.Wqkv, 3 * kD, kD, lw.sa.tc_qkv, c->allocs, terr) &&
+                 tc_prepare_weight(lw.sa.Wproj, kD, kD, lw.sa.tc_proj, c->allocs, terr) &&
+                 tc_prepare_weight(lw.W1, kFF, kD, lw.tc_w1, c->allocs, terr) &&
+                 tc_prepare_weight(lw.W2, kD, kFF, lw.tc_w2, c->allocs, terr);
+            if (ok && lw.cross)
+                ok = tc_prepare_weight(lw.Wq_c, kD, kD, lw.tc_q_c, c->allocs, terr) &&
+                     tc_prepare_weight(lw.Wkv_c, 2 * kD, kD, lw.tc_kv_c, c->allocs, terr) &&
+                     tc_prepare_weight(lw.Wproj_c, kD, kD, lw.tc_proj_c, c->allocs, terr);
+        }
+        // largest A operand: conv1 input view (NC*L1 rows x 2048) or FFN hidden (R x 768)
+        size_t max_a = std::max((size_t)NC * c->L[1] * c->conv[0].k * kD, R * (size_t)kFF);
+        if (ok) ok = tc_prepare_workspace(c->tcws, max_a, c->allocs, terr);
+        if (!ok) FAIL_CREATE(VAPB_ECUDA, "tcgen05 setup failed: %s", terr.c_str());
+    }
+
+    // taps (allocated lazily when keep_taps is switched on)
+    if (cudaDeviceSynchronize() != cudaSuccess) FAIL_CREATE(VAPB_ECUDA, "device error during create: %s", cudaGetErrorString(cudaGetLastError()));
+    *out = c;
+    return VAPB_OK;
+#undef FAIL_CREATE
+}
+
+int vapb_destroy(vapb_handle h) {
+    if (!h) return VAPB_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->ids_pinned) cudaFreeHost(h->ids_pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return VAPB_OK;
+}
+
+int vapb_chunk_samples(vapb_handle h) { return h ? h->S : VAPB_EINVAL; }
+
+int vapb_reset_streams(vapb_handle h, const int* ids, int n) {
+    if (!h) return VAPB_EINVAL;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    const size_t st = 2 * kD * sizeof(float), rg = (size_t)2 * h->T * kD * sizeof(float);
+    if (!ids || n <= 0) {
+        CK(h, cudaMemset(h->hS, 0, st * h->max_streams));
+        CK(h, cudaMemset(h->cS, 0, st * h->max_streams));
+        CK(h, cudaMemset(h->ring, 0, rg * h->max_streams));
+        CK(h, cudaMemset(h->count, 0, sizeof(int) * h->max_streams));
+        return VAPB_OK;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int id = ids[i];
+        if (id < 0 || id >= h->max_streams) return fail(h, VAPB_EINVAL, "stream id %d outside 0..%d", id, h->max_streams - 1);
+        CK(h, cudaMemset(h->hS + (size_t)id * 2 * kD, 0, st));
+        CK(h, cudaMemset(h->cS + (size_t)id * 2 * kD, 0, st));
+        CK(h, cudaMemset(h->ring + (size_t)id * 2 * h->T * kD, 0, rg));
+        CK(h, cudaMemset(h->count + id, 0, sizeof(int)));
+    }
+    return VAPB_OK;
+}
+
+int vapb_step(vapb_handle h, const float* audio, const int* ids, int B, float* out, void* cuda_stream) {
+    if (!h) return VAPB_EINVAL;
+    if (!audio || !out) return fail(h, VAPB_EINVAL, "audio/out is NULL");
+    int rc = check_ids(h, ids, B);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // ids -> device.  The pinned staging buffer is reused, so wait for the previous copy first.
+    if (h->last_B != 0) CK(h, cudaEventSynchronize(h->ev0));
+    memcpy(h->ids_pinned, ids, sizeof(int) * B);
+    CK(h, cudaMemcpyAsync(h->ids_dev, h->ids_pinned, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    CK(h, cudaEventRecord(h->ev0, st));
+    h->last_B = B;
+
+    const bool use_graph = h->opt_graph && !h->opt_keep_taps;
+    if (use_graph) {
+        GraphEntry* ge = nullptr;
+        for (auto& g : h->graphs)
+            if (g.B == B && g.audio == audio && g.out == out) ge = &g;
+        if (!ge) {
+            Step s{h, st, B, audio, out};
+            cudaGraph_t graph = nullptr;
+            CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            enqueue_step(s);
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (e != cudaSuccess || !graph) return fail(h, VAPB_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            cudaGraphExec_t exec = nullptr;
+            e = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return fail(h, VAPB_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+            if (h->graphs.size() >= 16) {
+                cudaGraphExecDestroy(h->graphs.front().exec);
+                h->graphs.erase(h->graphs.begin());
+            }
+            h->graphs.push_back(GraphEntry{B, audio, out, exec, s.n});
+            ge = &h->graphs.back();
+        }
+        CK(h, cudaGraphLaunch(ge->exec, st));
+        h->launches = ge->launches;
+    } else {
+        Step s{h, st, B, audio, out};
+        enqueue_step(s);
+        h->launches = s.n;
+        CK(h, cudaGetLastError());
+    }
+    if (h->opt_timing) {
+        CK(h, cudaEventRecord(h->ev1, st));
+        h->timed = true;
+    }
+    return VAPB_OK;
+}
+
+int vapb_step_host(vapb_handle h, const float* audio, const int* ids, int B, float* out, void* cuda_stream) {
+    if (!h) return VAPB_EINVAL;
+    if (B <= 0 || B > h->max_batch) return fail(h, VAPB_EINVAL, "B=%d outside 1..%d", B, h->max_batch);
+    if (!audio || !out) return fail(h, VAPB_EINVAL, "audio/out is NULL");
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    CK(h, cudaMemcpyAsync(h->audio_stage, audio, sizeof(float) * (size_t)B * 2 * h->S, cudaMemcpyHostToDevice, st));
+    int rc = vapb_step(h, h->audio_stage, ids, B, h->out_stage, cuda_stream);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(out, h->out_stage, sizeof(float) * (size_t)B * 6, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    return VAPB_OK;
+}
+
+size_t vapb_state_floats(vapb_handle h) { return h ? (size_t)2 + 4 * kD + (size_t)2 * h->T * kD : 0; }
+
+int vapb_export_state(vapb_handle h, int id, float* state) {
+    if (!h || !state) return VAPB_EINVAL;
+    if (id < 0 || id >= h->max_streams) return fail(h, VAPB_EINVAL, "stream id %d outside 0..%d", id, h->max_streams - 1);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    int cnt = 0;
+    CK(h, cudaMemcpy(&cnt, h->count + id, sizeof(int), cudaMemcpyDeviceToHost));
+    const int T = h->T, t = std::min(cnt, T);
+    state[0] = (float)cnt;
+    state[1] = (float)t;
+    CK(h, cudaMemcpy(state + 2, h->hS + (size_t)id * 2 * kD, 2 * kD * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(state + 2 + 2 * kD, h->cS + (size_t)id * 2 * kD, 2 * kD * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<float> raw((size_t)2 * T * kD);
+    CK(h, cudaMemcpy(raw.data(), h->ring + (size_t)id * 2 * T * kD, raw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    float* r = state + 2 + 4 * kD;
+    memset(r, 0, raw.size() * sizeof(float));
+    for (int ch = 0; ch < 2; ++ch)
+        for (int j = 0; j < t; ++j) {
+            const int slot = (cnt - t + j) % T;
+            memcpy(r + ((size_t)ch * T + j) * kD, raw.data() + ((size_t)ch * T + slot) * kD, kD * sizeof(float));
+        }
+    return VAPB_OK;
+}
+
+int vapb_import_state(vapb_handle h, int id, const float* state) {
+    if (!h || !state) return VAPB_EINVAL;
+    if (id < 0 || id >= h->max_streams) return fail(h, VAPB_EINVAL, "stream id %d outside 0..%d", id, h->max_streams - 1);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    const int T = h->T;
+    const int cnt = (int)state[0], t = (int)state[1];
+    if (cnt < 0 || t != std::min(cnt, T)) return fail(h, VAPB_EINVAL, "inconsistent state record (count %d, t %d, T %d)", cnt, t, T);
+    CK(h, cudaMemcpy(h->count + id, &cnt, sizeof(int), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->hS + (size_t)id * 2 * kD, state + 2, 2 * kD * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->cS + (size_t)id * 2 * kD, state + 2 + 2 * kD, 2 * kD * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> raw((size_t)2 * T * kD, 0.f);
+    const float* r = state + 2 + 4 * kD;
+    for (int ch = 0; ch < 2; ++ch)
+        for (int j = 0; j < t; ++j) {
+            const int slot = (cnt - t + j) % T;
+            memcpy(raw.data() + ((size_t)ch * T + slot) * kD, r + ((size_t)ch * T + j) * kD, kD * sizeof(float));
+        }
+    CK(h, cudaMemcpy(h->ring + (size_t)id * 2 * T * kD, raw.data(), raw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return VAPB_OK;
+}
+
+int vapb_set_option(vapb_handle h, const char* key, int value) {
+    if (!h || !key) return VAPB_EINVAL;
+    const std::string k(key);
+    if (k == "graph") h->opt_graph = value ? 1 : 0;
+    else if (k == "gemm") {
+        if (value != 0 && value != 1) return fail(h, VAPB_EINVAL, "gemm must be 0 or 1");
+        if (value != h->opt_gemm) {
+            cudaSetDevice(h->device);
+            cudaDeviceSynchronize();
+            for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+            h->graphs.clear();
+        }
+        h->opt_gemm = value;
+    } else if (k == "timing") h->opt_timing = value ? 1 : 0;
+    else if (k == "keep_taps") {
+        h->opt_keep_taps = value ? 1 : 0;
+        if (value && !h->tap_chan) {
+            CK(h, cudaSetDevice(h->device));
+            const size_t RX = (size_t)2 * h->max_batch * h->T * kD;
+            int rc = dalloc(h, &h->tap_xin, RX);
+            if (!rc) rc = dalloc(h, &h->tap_chan, RX);
+            for (int i = 0; i < 3 && !rc; ++i) rc = dalloc(h, &h->tap_cross[i], RX);
+            if (!rc) rc = dalloc(h, &h->tap_comb, (size_t)h->max_batch * kD);
+            if (!rc) rc = dalloc(h, &h->tap_logits, (size_t)h->max_batch * kD);
+            if (rc) return rc;
+        }
+    } else return fail(h, VAPB_EINVAL, "unknown option %s", key);
+    return VAPB_OK;
+}
+
+int vapb_get_option(vapb_handle h, const char* key, int* value) {
+    if (!h || !key || !value) return VAPB_EINVAL;
+    const std::string k(key);
+    if (k == "graph") *value = h->opt_graph;
+    else if (k == "gemm") *value = h->opt_gemm;
+    else if (k == "timing") *value = h->opt_timing;
+    else if (k == "keep_taps") *value = h->opt_keep_taps;
+    else return fail(h, VAPB_EINVAL, "unknown option %s", key);
+    return VAPB_OK;
+}
+
+int vapb_debug_tensor(vapb_handle h, const char* name, float* host_out, size_t cap, size_t* n_out) {
+    if (!h || !name || !n_out) return VAPB_EINVAL;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    const int B = h->last_B, NC = 2 * B;
+    if (B == 0) return fail(h, VAPB_EINVAL, "no step has run yet");
+    const std::string k(name);
+    const size_t RX = (size_t)NC * h->T * kD;
+    const float* src = nullptr;
+    size_t n = 0;
+    std::vector<float> tmp;
+    if (k.size() == 5 && k.compare(0, 4, "conv") == 0 && k[4] >= '0' && k[4] <= '4') {
+        // strip the halo rows: [NC][L][256]
+        const int i = k[4] - '0';
+        const size_t rows = (size_t)h->L[i] + 2 * h->halo[i];
+        std::vector<float> raw((size_t)NC * rows * kD);
+        CK(h, cudaMemcpy(raw.data(), h->act[i], raw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        tmp.resize((size_t)NC * h->L[i] * kD);
+        for (int c = 0; c < NC; ++c)
+            memcpy(tmp.data() + (size_t)c * h->L[i] * kD, raw.data() + ((size_t)c * rows + h->halo[i]) * kD,
+                   (size_t)h->L[i] * kD * sizeof(float));
+        n = tmp.size();
+    } else if (k == "lstm_out") { src = h->Y; n = (size_t)NC * h->n_lstm * kD; }
+    else if (k == "e") { src = h->ebuf; n = (size_t)NC * kD; }
+    else if (k == "x_out") { src = h->X; n = RX; }
+    else if (h->opt_keep_taps && k == "x_in") { src = h->tap_xin; n = RX; }
+    else if (h->opt_keep_taps && k == "chan_out") { src = h->tap_chan; n = RX; }
+    else if (h->opt_keep_taps && k.size() == 10 && k.compare(0, 5, "cross") == 0 && k.compare(6, 4, "_out") == 0 && k[5] >= '0' && k[5] <= '2') {
+        src = h->tap_cross[k[5] - '0']; n = RX;
+    } else if (h->opt_keep_taps && k == "comb") { src = h->tap_comb; n = (size_t)B * kD; }
+    else if (h->opt_keep_taps && k == "logits") { src = h->tap_logits; n = (size_t)B * kD; }
+    else return fail(h, VAPB_EINVAL, "unknown tap %s (or keep_taps is off)", name);
+    *n_out = n;
+    if (!host_out) return VAPB_OK;
+    if (cap < n) return fail(h, VAPB_EINVAL, "tap %s needs %zu floats, buffer has %zu", name, n, cap);
+    if (src) CK(h, cudaMemcpy(host_out, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+    else memcpy(host_out, tmp.data(), n * sizeof(float));
+    return VAPB_OK;
+}
+
+int vapb_last_launch_count(vapb_handle h) { return h ? h->launches : VAPB_EINVAL; }
+
+int vapb_last_step_ms(vapb_handle h, float* ms) {
+    if (!h || !ms) return VAPB_EINVAL;
+    if (!h->timed) return fail(h, VAPB_EINVAL, "option timing is off or no step has run");
+    CK(h, cudaEventSynchronize(h->ev1));
+    CK(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return VAPB_OK;
+}
+
+int vapb_profile_step(vapb_handle h, const float* audio, const int* ids, int B, float* out, void* cuda_stream,
+                      char* report, size_t cap) {
+    if (!h) return VAPB_EINVAL;
+    if (!audio || !out || !report || cap == 0) return fail(h, VAPB_EINVAL, "null argument");
+    int rc = check_ids(h, ids, B);
+    if (rc) return rc;
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    CK(h, cudaStreamSynchronize(st));
+    memcpy(h->ids_pinned, ids, sizeof(int) * B);
+    CK(h, cudaMemcpyAsync(h->ids_dev, h->ids_pinned, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    h->last_B = B;
+    std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    Step s{h, st, B, audio, out};
+    s.prof = &ev;
+    cudaEvent_t e0;
+    cudaEventCreate(&e0);
+    cudaEventRecord(e0, st);
+    CK(h, cudaEventRecord(h->ev0, st));
+    enqueue_step(s);
+    h->launches = s.n;
+    cudaError_t e = cudaStreamSynchronize(st);
+    std::vector<std::pair<std::string, std::pair<float, int>>> agg;
+    cudaEvent_t prev = e0;
+    float total = 0.f;
+    for (auto& pr : ev) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, prev, pr.second);
+        total += ms;
+        bool found = false;
+        for (auto& a : agg)
+            if (a.first == pr.first) { a.second.first += ms; a.second.second += 1; found = true; }
+        if (!found) agg.push_back({pr.first, {ms, 1}});
+        prev = pr.second;
+    }
+    cudaEventDestroy(e0);
+    for (auto& pr : ev) cudaEventDestroy(pr.second);
+    if (e != cudaSuccess) return fail(h, VAPB_ECUDA, "profile step failed: %s", cudaGetErrorString(e));
+    std::string rep = "tag,launches,ms\n";
+    char line[160];
+    for (auto& a : agg) {
+        snprintf(line, sizeof line, "%s,%d,%.6f\n", a.first.c_str(), a.second.second, a.second.first);
+        rep += line;
+    }
+    snprintf(line, sizeof line, "total,%d,%.6f\n", (int)ev.size(), total);
+    rep += line;
+    snprintf(report, cap, "%s", rep.c_str());
+    return VAPB_OK;
+}
+
+int vapb_selftest_gemm(int device, int variant, double* max_rel_err) {
+    std::string err;
+    int rc = tc_selftest(device, variant, max_rel_err, err);
+    g_create_error = err;      // the report (also on success) is readable through vapb_last_error(NULL)
+    return rc;
+}
+
+}  // extern "C"
