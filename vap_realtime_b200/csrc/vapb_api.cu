@@ -119,6 +119,10 @@ struct vapb_ctx {
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    // CUDA graphs cannot be captured on the legacy default stream: work submitted on it is
+    // bridged onto this internal stream with events (stream order is preserved for the caller).
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -592,6 +596,10 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         FAIL_CREATE(VAPB_ENOMEM, "cudaMallocHost failed");
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        FAIL_CREATE(VAPB_ECUDA, "cudaStreamCreate failed");
 
     // ---- tcgen05 operands: bf16 hi/lo planes of every tensor-core GEMM weight (+ workspaces)
     {
@@ -632,6 +640,9 @@ int vapb_destroy(vapb_handle h) {
     if (h->ids_pinned) cudaFreeHost(h->ids_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return VAPB_OK;
 }
@@ -667,7 +678,15 @@ int vapb_step(vapb_handle h, const float* audio, const int* ids, int B, float* o
     int rc = check_ids(h, ids, B);
     if (rc) return rc;
     CK(h, cudaSetDevice(h->device));
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t caller = static_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t st = caller;
+    const bool use_graph = h->opt_graph && !h->opt_keep_taps;
+    const bool bridge = use_graph && (caller == nullptr || caller == cudaStreamLegacy || caller == cudaStreamPerThread);
+    if (bridge) {
+        st = h->own_stream;
+        CK(h, cudaEventRecord(h->ev_in, caller));
+        CK(h, cudaStreamWaitEvent(st, h->ev_in, 0));
+    }
     // ids -> device.  The pinned staging buffer is reused, so wait for the previous copy first.
     if (h->last_B != 0) CK(h, cudaEventSynchronize(h->ev0));
     memcpy(h->ids_pinned, ids, sizeof(int) * B);
@@ -675,7 +694,6 @@ int vapb_step(vapb_handle h, const float* audio, const int* ids, int B, float* o
     CK(h, cudaEventRecord(h->ev0, st));
     h->last_B = B;
 
-    const bool use_graph = h->opt_graph && !h->opt_keep_taps;
     if (use_graph) {
         GraphEntry* ge = nullptr;
         for (auto& g : h->graphs)
@@ -709,6 +727,10 @@ int vapb_step(vapb_handle h, const float* audio, const int* ids, int B, float* o
     if (h->opt_timing) {
         CK(h, cudaEventRecord(h->ev1, st));
         h->timed = true;
+    }
+    if (bridge) {
+        CK(h, cudaEventRecord(h->ev_out, st));
+        CK(h, cudaStreamWaitEvent(caller, h->ev_out, 0));
     }
     return VAPB_OK;
 }
