@@ -384,8 +384,8 @@ constexpr int kAttnWarps = 8;
 __global__ void __launch_bounds__(kAttnWarps * 32) k_attention(AttnArgs a) {
     extern __shared__ float smem[];
     const int T = a.T;
-    float* sK = smem;                       // [T][65]
-    float* sV = sK + T * 65;                // [T][64]
+    float* sK = smem;                       // [T][65] (row pitch 65 floats: conflict-free q.k dots)
+    float* sV = sK + ((T * 65 + 3) & ~3);   // [T][64], 16-byte aligned for float4 stores
     float* sQ = sV + T * 64;                // [warps][64]
     float* sP = sQ + kAttnWarps * 64;       // [warps][128]
     const int n = blockIdx.x, h = blockIdx.y;
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) k_attention(AttnArgs a) {
     }
 }
 void launch_attention(const AttnArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)(a.T * 65 + a.T * 64 + kAttnWarps * 64 + kAttnWarps * 128) * sizeof(float);
+    const size_t smem = (size_t)(((a.T * 65 + 3) & ~3) + a.T * 64 + kAttnWarps * 64 + kAttnWarps * 128) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
