@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.samples, self.reasons = [], set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
             "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
             "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -113,7 +113,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.01)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         return {
             "sm_mhz": float(np.median(self.samples)) if self.samples else None,
