@@ -34,7 +34,11 @@ def replay(engine, audio, n, ids=None):
     return np.array(outs)
 
 
-@pytest.mark.parametrize("variant", range(6))
+# case + 16 * tile selector (0 = automatic, 1/2/3 = force N tile 64/128/256)
+SELFTEST_VARIANTS = list(range(6)) + [16 + 0, 16 + 2, 16 + 5, 32 + 1, 32 + 4, 32 + 5, 48 + 0, 48 + 2, 48 + 3]
+
+
+@pytest.mark.parametrize("variant", SELFTEST_VARIANTS)
 def test_tcgen05_gemm_selftest(variant):
     err, report = selftest_gemm(variant)
     print(report)
@@ -165,6 +169,26 @@ def test_ragged_batch_random_weights(gemm, bc):
             local[k] += 1
     print("ragged batch: max|d| =", worst)
     assert worst < TOL[gemm]
+
+
+def test_option_variants_agree(vap_weights, fixture_audio):
+    """Fused cluster LSTM vs per-step GEMM LSTM, and every tcgen05 N-tile width, give the same answer."""
+    audio, ref = fixture_audio
+    outs = {}
+    for name, opts in {"default": {}, "lstm_unfused": {"lstm_fused": 0}, "tile64": {"tile_n": 64},
+                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}}.items():
+        eng = VapEngine(vap_weights, 20, 50, max_streams=3)
+        eng.set_option("gemm", DEF)
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        a3 = np.stack([audio[:, 4000 * k: 4000 * k + 800 * 70 + 320] for k in range(3)])
+        outs[name] = np.array([eng.step(torch.from_numpy(np.ascontiguousarray(chunk(a3, n))).cuda()).cpu().numpy()
+                               for n in range(70)])
+        print(name, "max|d| vs reference fixture (stream 0):", np.abs(outs[name][:, 0] - ref[:70]).max())
+        assert np.abs(outs[name][:, 0] - ref[:70]).max() < TOL[DEF]
+    for name in outs:
+        assert np.abs(outs[name] - outs["default"]).max() < 2e-5, name
+    assert np.array_equal(outs["tile64"], outs["tile256"])        # tile width does not change a row's arithmetic
 
 
 def test_graph_equals_eager(vap_weights, fixture_audio):

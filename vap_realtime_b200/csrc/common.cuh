@@ -65,6 +65,8 @@ void launch_scatter_state(float* hS, float* cS, const int* ids, const float* hW,
                           cudaStream_t st);
 void launch_lstm_cell(const float* G, float* hW, float* cW, float* Y, int n_rows, int n_steps, int step,
                       cudaStream_t st);
+void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* cS, const int* ids, float* Y, int NC,
+                           int n_steps, cudaStream_t st);
 void launch_ln_gelu_ring(const float* X, int B, const float* w, const float* b, float* ring,
                          const int* count, const int* ids, int T, float* e_out, cudaStream_t st);
 void launch_gather_ring(const float* ring, const int* count, const int* ids, float* X, int* tvalid, int B,

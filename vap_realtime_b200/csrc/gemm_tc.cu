@@ -21,16 +21,18 @@ namespace {
 constexpr int kBM = 128;          // rows per CTA tile = UMMA M
 constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kProducerWarps = 8; // A producers, afterwards the epilogue
+constexpr int kThreads = (kProducerWarps + 2) * 32;   // + TMA warp + MMA warp
 constexpr int kATile = kBM * kBK * 2;     // bytes per A plane per stage (16 KB)
+constexpr int kEpiPitch = 33;             // floats per row of the per-warp epilogue transpose buffer
 
 template <int BN>
 struct Cfg {
     static constexpr int kWTile = BN * kBK * 2;                       // bytes per W plane per stage
     static constexpr int kStageBytes = 2 * kATile + 2 * kWTile;
-    static constexpr int kStages = (BN == 256) ? 2 : 3;
+    static constexpr int kStages = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(kProducerWarps * 32 * kEpiPitch * 4 <= kStageBytes, "epilogue staging must fit in stage 0");
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -141,12 +143,44 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
 }
 
 // ---- the kernel -----------------------------------------------------------------------
+__device__ __forceinline__ void load_a_rows(const float* const (&rowp)[4], int kb, float4 (&v)[4][2]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (rowp[i]) {
+            const float4* p = reinterpret_cast<const float4*>(rowp[i] + (size_t)kb * kBK);
+            v[i][0] = __ldg(p);
+            v[i][1] = __ldg(p + 1);
+        } else {
+            v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i][1] = v[i][0];
+        }
+    }
+}
+
+__device__ __forceinline__ void store_a_rows(const float4 (&v)[4][2], uint32_t a_hi, uint32_t a_lo, int r0, int chunk) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        uint32_t h[4], l[4];
+        split2(v[i][0].x, v[i][0].y, h[0], l[0]);
+        split2(v[i][0].z, v[i][0].w, h[1], l[1]);
+        split2(v[i][1].x, v[i][1].y, h[2], l[2]);
+        split2(v[i][1].z, v[i][1].w, h[3], l[3]);
+        const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(chunk ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3])
+                     : "memory");
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024 B alignment
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + C::kStages * C::kStageBytes;
     // barrier slots: full[s] at bars + 8*s, empty[s] at bars + 8*(kStages+s), accum at bars + 16*kStages, tmem ptr after
     const uint32_t bar_accum = bars + 16 * C::kStages;
@@ -162,103 +196,98 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
     const int nkb = g.K / kBK;
 
-    if (warp == 4 && lane == 0) {
+    if (warp == kProducerWarps && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(full_bar(s), 4 + 1);       // 4 producer warps + the TMA thread's expect_tx arrive
-            mbar_init(empty_bar(s), 1);          // one tcgen05.commit
+            mbar_init(full_bar(s), kProducerWarps + 1);   // producer warps + the TMA thread's expect_tx arrive
+            mbar_init(empty_bar(s), 1);                   // one tcgen05.commit
         }
         mbar_init(bar_accum, 1);
         fence_barrier_init();
         prefetch_tmap(&map_hi);
         prefetch_tmap(&map_lo);
     }
-    if (warp == 5) tmem_alloc(tmem_slot, BN);
+    if (warp == kProducerWarps + 1) tmem_alloc(tmem_slot, BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp < 4) {
+    if (warp < kProducerWarps) {
         // ================= A producers =================
         const int chunk = tid & 7;                     // 16-byte chunk (8 bf16) within the 128-byte row
-        const int r0 = tid >> 3;                       // rows r0 + 16*i
-        const float* rowp[8];
+        const int r0 = tid >> 3;                       // rows r0 + 32*i
+        const float* rowp[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m0 + r0 + 16 * i;
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + r0 + 32 * i;
             rowp[i] = (m < g.M) ? (g.A + rowmap_off(g.amap, m) + chunk * 8) : nullptr;
         }
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % C::kStages;
-            const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
-            float4 v[8][2];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (rowp[i]) {
-                    const float4* p = reinterpret_cast<const float4*>(rowp[i] + (size_t)kb * kBK);
-                    v[i][0] = __ldg(p);
-                    v[i][1] = __ldg(p + 1);
-                } else {
-                    v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[i][1] = v[i][0];
-                }
+        // software pipeline: the loads of k-block kb+1 are in flight while kb is split and stored
+        float4 va[4][2], vb[4][2];
+        load_a_rows(rowp, 0, va);
+        for (int kb = 0; kb < nkb; kb += 2) {
+            {
+                const int s = kb % C::kStages;
+                const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
+                if (kb + 1 < nkb) load_a_rows(rowp, kb + 1, vb);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                store_a_rows(va, a_hi(s), a_lo(s), r0, chunk);
+                fence_proxy_async();                  // generic-proxy smem writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
             }
-            mbar_wait(empty_bar(s), ph ^ 1u);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 16 * i;
-                uint32_t h[4], l[4];
-                split2(v[i][0].x, v[i][0].y, h[0], l[0]);
-                split2(v[i][0].z, v[i][0].w, h[1], l[1]);
-                split2(v[i][1].x, v[i][1].y, h[2], l[2]);
-                split2(v[i][1].z, v[i][1].w, h[3], l[3]);
-                const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(chunk ^ (r & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi(s) + off), "r"(h[0]), "r"(h[1]), "r"(h[2]),
-                             "r"(h[3])
-                             : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo(s) + off), "r"(l[0]), "r"(l[1]), "r"(l[2]),
-                             "r"(l[3])
-                             : "memory");
+            if (kb + 1 < nkb) {
+                const int s = (kb + 1) % C::kStages;
+                const uint32_t ph = (uint32_t)((kb + 1) / C::kStages) & 1u;
+                if (kb + 2 < nkb) load_a_rows(rowp, kb + 2, va);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                store_a_rows(vb, a_hi(s), a_lo(s), r0, chunk);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
             }
-            fence_proxy_async();                      // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
         }
         // ================= epilogue =================
+        // TMEM lane quadrant = warp % 4 (hardware rule), column half = warp / 4.  Each 32x32 block is
+        // transposed through a private smem buffer so that global reads/writes are 128-byte coalesced.
+        const int quad = warp & 3, half = warp >> 2;
+        constexpr int kChunks = BN / 64;               // 32-column chunks per warp
+        const int row_l = quad * 32 + lane;            // accumulator row owned by this thread (TMEM lane)
+        const int m_own = m0 + row_l;
+        long long coff_own = 0, roff_own = 0;
+        if (m_own < g.M) {
+            coff_own = rowmap_off(g.cmap, m_own);
+            if (g.R) roff_own = rowmap_off(g.rmap, m_own);
+        }
+        const int rows_valid = min(32, g.M - (m0 + quad * 32));     // rows of this warp's quadrant inside M
+        float* tbuf = reinterpret_cast<float*>(base_ptr) + warp * (32 * kEpiPitch);
         mbar_wait(bar_accum, 0);
         tc_fence_after();
-        const int m = m0 + warp * 32 + lane;           // TMEM lane == accumulator row
-        const bool valid = m < g.M;
-        float* crow = valid ? (g.C + rowmap_off(g.cmap, m)) : nullptr;
-        const float* rrow = (valid && g.R) ? (g.R + rowmap_off(g.rmap, m)) : nullptr;
 #pragma unroll 1
-        for (int cb = 0; cb < BN / 32; ++cb) {
+        for (int cb = 0; cb < kChunks; ++cb) {
+            const int col0 = half * (BN / 2) + cb * 32;
             uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), raw);
-            if (valid) {
-                const int n = n0 + cb * 32;
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, raw);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float x[4] = {__uint_as_float(raw[4 * q + 0]), __uint_as_float(raw[4 * q + 1]),
-                                  __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3])};
-                    if (g.bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4 * q));
-                        x[0] += bb.x; x[1] += bb.y; x[2] += bb.z; x[3] += bb.w;
-                    }
-                    if (g.act == 1) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) x[e] = gelu_erf(x[e]);
-                    }
-                    if (rrow) {
-                        const float4 rr = *reinterpret_cast<const float4*>(rrow + n + 4 * q);
-                        x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
-                    }
-                    *reinterpret_cast<float4*>(crow + n + 4 * q) = make_float4(x[0], x[1], x[2], x[3]);
+            for (int c = 0; c < 32; ++c) tbuf[lane * kEpiPitch + c] = __uint_as_float(raw[c]);
+            __syncwarp();
+            const int n = n0 + col0 + lane;
+            const float bias = g.bias ? __ldg(g.bias + n) : 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+                const long long coff = __shfl_sync(0xffffffffu, coff_own, rr);
+                const long long roff = __shfl_sync(0xffffffffu, roff_own, rr);
+                if (rr < rows_valid) {
+                    float x = tbuf[rr * kEpiPitch + lane] + bias;
+                    if (g.act == 1) x = gelu_erf(x);
+                    if (g.R) x += g.R[roff + n];
+                    g.C[coff + n] = x;
                 }
             }
+            __syncwarp();
         }
-    } else if (warp == 4) {
+    } else if (warp == kProducerWarps) {
         // ================= TMA producer (W planes) =================
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
@@ -295,7 +324,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, BN);
+    if (warp == kProducerWarps + 1) tmem_dealloc(tmem_base, BN);
 }
 
 // fp32 [n] -> bf16 hi / lo planes
@@ -342,7 +371,7 @@ bool encode_plane(CUtensorMap* map, void* ptr, int N, int K, int box_n, std::str
     return true;
 }
 
-int pick_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+constexpr int kTileN[3] = {64, 128, 256};
 
 template <int BN>
 bool ensure_attr(std::string* err) {
@@ -364,7 +393,7 @@ bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vec
         err = "tc_prepare_weight: null weight";
         return false;
     }
-    if (K % kBK != 0 || N % 128 != 0) {
+    if (K % kBK != 0 || N % 64 != 0) {
         err = "tc_prepare_weight: unsupported shape";
         return false;
     }
@@ -380,31 +409,54 @@ bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vec
     out.lo = static_cast<__nv_bfloat16*>(lo);
     out.N = N;
     out.K = K;
-    out.block_n = pick_block_n(N);
     k_split_planes<<<(unsigned)((n + 255) / 256), 256>>>(W_dev, out.hi, out.lo, n);
     if (cudaGetLastError() != cudaSuccess) {
         err = "k_split_planes launch failed";
         return false;
     }
-    if (!encode_plane(&out.map_hi, hi, N, K, out.block_n, err)) return false;
-    if (!encode_plane(&out.map_lo, lo, N, K, out.block_n, err)) return false;
-    if (!ensure_attr<128>(&err) || !ensure_attr<256>(&err)) return false;
+    for (int t = 0; t < 3; ++t) {
+        out.has_tile[t] = (N % kTileN[t] == 0);
+        if (!out.has_tile[t]) continue;
+        if (!encode_plane(&out.map_hi[t], hi, N, K, kTileN[t], err)) return false;
+        if (!encode_plane(&out.map_lo[t], lo, N, K, kTileN[t], err)) return false;
+    }
+    if (!ensure_attr<64>(&err) || !ensure_attr<128>(&err) || !ensure_attr<256>(&err)) return false;
     return true;
 }
 
 bool tc_prepare_workspace(TcWorkspace&, size_t, std::vector<void*>&, std::string&) { return true; }
 
-int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace&, cudaStream_t st) {
-    dim3 grid((g.M + kBM - 1) / kBM, g.N / w.block_n);
-    if (w.block_n == 256)
-        k_gemm_tc<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(g, w.map_hi, w.map_lo);
+// Tile width: the widest N tile that still puts a CTA on (nearly) every SM; small problems take narrow tiles.
+int pick_tile(const GemmArgs& g, const TcWeight& w, int force_bn) {
+    const int mt = (g.M + kBM - 1) / kBM;
+    if (force_bn)
+        for (int t = 0; t < 3; ++t)
+            if (kTileN[t] == force_bn && w.has_tile[t]) return t;
+    for (int t = 2; t >= 0; --t)
+        if (w.has_tile[t] && mt * (g.N / kTileN[t]) >= 132) return t;
+    for (int t = 0; t < 3; ++t)
+        if (w.has_tile[t]) return t;
+    return 1;
+}
+
+int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace& ws, cudaStream_t st) {
+    const int t = pick_tile(g, w, ws.force_bn);
+    dim3 grid((g.M + kBM - 1) / kBM, g.N / kTileN[t]);
+    if (t == 2)
+        k_gemm_tc<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);
+    else if (t == 1)
+        k_gemm_tc<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);
     else
-        k_gemm_tc<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(g, w.map_hi, w.map_lo);
+        k_gemm_tc<64><<<grid, kThreads, Cfg<64>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);
     return 1;
 }
 
 // ---- self test --------------------------------------------------------------------------
 int tc_selftest(int device, int variant, double* max_rel_err, std::string& report) {
+    // variant = case + 16 * tile selector (0 = automatic, 1/2/3 = force BN 64/128/256)
+    const int tsel = variant / 16;
+    variant %= 16;
+    const int force_bn = tsel == 0 ? 0 : kTileN[tsel - 1];
     struct Case { int M, N, K; int conv; int bias, act, resid; };
     // conv: A is a channels-last chunked view with overlapping rows (conv1 geometry: k=8, s=4, pad=2, L 224 -> 56)
     static const Case cases[] = {
@@ -473,6 +525,7 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
         launch_sgemm(g, 0);
         g.C = dC1;
         TcWorkspace ws;
+        ws.force_bn = force_bn;
         launch_gemm_tc(g, tw, ws, 0);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
@@ -498,7 +551,7 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
         snprintf(buf, sizeof buf,
                  "variant %d M=%d N=%d K=%d BN=%d: max|ref|=%.4g max|diff|=%.4g rel=%.3g nbad=%zu worst@(%zu,%zu) ref=%.6g tc=%.6g; "
                  "C[0][0..3] ref=%.5g %.5g %.5g %.5g tc=%.5g %.5g %.5g %.5g",
-                 variant, M, N, K, tw.block_n, maxabs, maxdiff, *max_rel_err, nbad, worst / N, worst % N, c0[worst], c1[worst],
+                 variant, M, N, K, force_bn, maxabs, maxdiff, *max_rel_err, nbad, worst / N, worst % N, c0[worst], c1[worst],
                  c0[0], c0[1], c0[2], c0[3], c1[0], c1[1], c1[2], c1[3]);
         report = buf;
     }

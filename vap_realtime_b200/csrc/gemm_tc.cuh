@@ -28,12 +28,12 @@ struct TcWeight {
     __nv_bfloat16* hi = nullptr;     // [N][K]
     __nv_bfloat16* lo = nullptr;     // [N][K]
     int N = 0, K = 0;
-    int block_n = 0;                 // N tile the tensor maps were encoded for
-    CUtensorMap map_hi, map_lo;      // 2D {K, N}, box {64, block_n}, SWIZZLE_128B
+    bool has_tile[3] = {false, false, false};      // N tile widths 64 / 128 / 256
+    CUtensorMap map_hi[3], map_lo[3];              // 2D {K, N}, box {64, tile}, SWIZZLE_128B
 };
 
 struct TcWorkspace {
-    int dummy = 0;
+    int force_bn = 0;                // 0 = pick the tile width from the grid size, else 64 / 128 / 256
 };
 
 // Splits W (device fp32 [N][K]) into bf16 planes and encodes the TMA descriptors.

@@ -27,6 +27,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// one 256-wide fp32 row spread over a warp: lane owns columns {4*lane..+3, 128+4*lane..+3}
+__device__ __forceinline__ void load_row8(const float* p, int lane, float v[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p + lane * 4);
+    const float4 b = *reinterpret_cast<const float4*>(p + 128 + lane * 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store_row8(float* p, int lane, const float v[8]) {
+    *reinterpret_cast<float4*>(p + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
 
 // -----------------------------------------------------------------------------------------
 // conv0 (1 -> 256, k=10, s=5, p=3) + ChannelNorm + ReLU, channels-last output.
@@ -36,7 +46,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 constexpr int kC0PosPerBlock = 56;
 
 __global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__ audio, int S, int L0,
-                                                       const float* __restrict__ w,    // [256][10]
+                                                       const float* __restrict__ w,    // [10][256] tap-major
                                                        const float* __restrict__ b,
                                                        const float* __restrict__ cnw,
                                                        const float* __restrict__ cnb,
@@ -53,18 +63,17 @@ __global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__
         s_in[i] = (s >= 0 && s < S) ? a[s] : 0.0f;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int ch[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ch[i] = (i < 4) ? (lane * 4 + i) : (128 + lane * 4 + (i - 4));
     float wr[8][10], br[8], gw[8], gb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int k = 0; k < 10; ++k) {          // coalesced float4 loads of the tap-major weights
+        float t[8];
+        load_row8(w + k * 256, lane, t);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) wr[i][k] = w[ch[i] * 10 + k];
-        br[i] = b[ch[i]];
-        gw[i] = cnw[ch[i]];
-        gb[i] = cnb[ch[i]];
+        for (int i = 0; i < 8; ++i) wr[i][k] = t[i];
     }
+    load_row8(b, lane, br);
+    load_row8(cnw, lane, gw);
+    load_row8(cnb, lane, gb);
     __syncthreads();
     for (int p = warp; p < npos; p += 8) {
         float x[10];
@@ -189,9 +198,92 @@ __global__ void __launch_bounds__(256) k_sgemm(GemmArgs g) {
     }
 }
 
+// Small-problem variant: 64x64x32 tiles (4x more CTAs, 4x fewer, fatter k-iterations) for the
+// latency-bound shapes (LSTM input projection M = 2B*5, anything with a handful of 128-row tiles).
+constexpr int SM_ = 64, SN_ = 64, SK_ = 32, SLD = 68;
+
+__global__ void __launch_bounds__(256) k_sgemm64(GemmArgs g) {
+    __shared__ __align__(16) float As[2][SK_][SLD];
+    __shared__ __align__(16) float Bs[2][SK_][SLD];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * SM_, n0 = blockIdx.y * SN_;
+    // loader: thread -> (row lr = tid / 4 (0..63), k quads kq = (tid % 4) * 4 and + 16)
+    const int lr = tid >> 2, kq = (tid & 3) * 4;
+    const int am = m0 + lr;
+    const float* aptr = (am < g.M) ? (g.A + rowmap_off(g.amap, am) + kq) : nullptr;
+    const float* wptr = g.W + (size_t)(n0 + lr) * g.K + kq;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ra0, ra1, rw0, rw1;
+    auto gload = [&](int kt) {
+        const size_t o = (size_t)kt * SK_;
+        ra0 = aptr ? __ldg(reinterpret_cast<const float4*>(aptr + o)) : z4;
+        ra1 = aptr ? __ldg(reinterpret_cast<const float4*>(aptr + o + 16)) : z4;
+        rw0 = __ldg(reinterpret_cast<const float4*>(wptr + o));
+        rw1 = __ldg(reinterpret_cast<const float4*>(wptr + o + 16));
+    };
+    auto sstore = [&](int buf) {
+        As[buf][kq + 0][lr] = ra0.x; As[buf][kq + 1][lr] = ra0.y; As[buf][kq + 2][lr] = ra0.z; As[buf][kq + 3][lr] = ra0.w;
+        As[buf][kq + 16][lr] = ra1.x; As[buf][kq + 17][lr] = ra1.y; As[buf][kq + 18][lr] = ra1.z; As[buf][kq + 19][lr] = ra1.w;
+        Bs[buf][kq + 0][lr] = rw0.x; Bs[buf][kq + 1][lr] = rw0.y; Bs[buf][kq + 2][lr] = rw0.z; Bs[buf][kq + 3][lr] = rw0.w;
+        Bs[buf][kq + 16][lr] = rw1.x; Bs[buf][kq + 17][lr] = rw1.y; Bs[buf][kq + 18][lr] = rw1.z; Bs[buf][kq + 19][lr] = rw1.w;
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, 4 x 4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int nk = g.K / SK_;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int cur = kt & 1;
+        if (kt + 1 < nk) gload(kt + 1);
+#pragma unroll
+        for (int k = 0; k < SK_; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) sstore(cur ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+        const int n = n0 + tx * 4;
+        float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+        if (g.bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+            v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+        }
+        if (g.act == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = gelu_erf(v[q]);
+        }
+        if (g.R) {
+            const float4 rr = *reinterpret_cast<const float4*>(g.R + rowmap_off(g.rmap, m) + n);
+            v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+        }
+        *reinterpret_cast<float4*>(g.C + rowmap_off(g.cmap, m) + n) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 void launch_sgemm(const GemmArgs& g, cudaStream_t st) {
-    dim3 grid((g.M + BM - 1) / BM, g.N / BN);
-    k_sgemm<<<grid, 256, 0, st>>>(g);
+    const int big_ctas = ((g.M + BM - 1) / BM) * (g.N / BN);
+    if (big_ctas < 100 && g.K % SK_ == 0) {
+        dim3 grid((g.M + SM_ - 1) / SM_, g.N / SN_);
+        k_sgemm64<<<grid, 256, 0, st>>>(g);
+    } else {
+        dim3 grid((g.M + BM - 1) / BM, g.N / BN);
+        k_sgemm<<<grid, 256, 0, st>>>(g);
+    }
 }
 
 // -----------------------------------------------------------------------------------------
@@ -199,15 +291,6 @@ void launch_sgemm(const GemmArgs& g, cudaStream_t st) {
 // LayerNorm(256) (+ optional GELU) (modules.py:242-243, 268; encoder_components.py:408-428).
 // One warp per row; lane owns columns {4*lane.., 128+4*lane..}.
 // -----------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_row8(const float* p, int lane, float v[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p + lane * 4);
-    const float4 b = *reinterpret_cast<const float4*>(p + 128 + lane * 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void store_row8(float* p, int lane, const float v[8]) {
-    *reinterpret_cast<float4*>(p + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 128 + lane * 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
 // normalise v[8] (one 256-wide row spread over a warp); denom = 255 (unbiased) or 256 (biased)
 __device__ __forceinline__ void warp_norm8(float v[8], float denom_inv, const float* w, const float* b, int lane) {
     float s = 0.f;
@@ -319,6 +402,141 @@ void launch_lstm_cell(const float* G, float* hW, float* cW, float* Y, int n_rows
                       cudaStream_t st) {
     const int n = n_rows * kD;
     k_lstm_cell<<<(n + 255) / 256, 256, 0, st>>>(G, hW, cW, Y, n_rows, n_steps, step);
+}
+
+// -----------------------------------------------------------------------------------------
+// Fused LSTM recurrence (encoder_components.py:120-123, 140-153): all n_steps of
+//   g = Gx[:, t] + W_hh h ;  c = sig(f) c + sig(i) tanh(g~) ;  h = sig(o) tanh(c)
+// in ONE kernel, true fp32.  A thread-block cluster of 8 CTAs owns a tile of kLstmRT rows
+// (channel-chunks); CTA r owns hidden units [32r, 32r+32) = 128 gate columns whose W_hh slice
+// (128 KB) stays resident in shared memory for every step.  After each step the new h slices
+// are exchanged through distributed shared memory (st to the 8 peers) + one cluster barrier.
+// Also replaces the gather/scatter of the per-stream (h, c) state.
+// -----------------------------------------------------------------------------------------
+constexpr int kLstmRT = 16;
+constexpr int kLstmWPitch = 129;
+constexpr int kLstmGPitch = 132;
+constexpr size_t kLstmSmem = (size_t)(256 * kLstmWPitch + 2 * kLstmRT * kD + kLstmRT * kLstmGPitch + kLstmRT * 32) * sizeof(float);
+
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256)
+k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih z + b_ih + b_hh
+                 const float* __restrict__ Whh,     // [1024][256]
+                 float* hS, float* cS, const int* __restrict__ ids,
+                 float* __restrict__ Y,             // [NC][n_steps][256]
+                 int NC, int n_steps) {
+    extern __shared__ float lsm[];
+    float* sW = lsm;                                   // [256 k][129]  (col = gate*32 + unit)
+    float* sH = sW + 256 * kLstmWPitch;                // [2][RT][256]
+    float* sG = sH + 2 * kLstmRT * kD;                 // [RT][132]
+    float* sC = sG + kLstmRT * kLstmGPitch;            // [RT][32]
+    unsigned crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = (blockIdx.x >> 3) * kLstmRT;
+
+    // W_hh slice -> smem: for each of the 128 local columns, 256 contiguous k (coalesced read)
+    for (int col = warp; col < 128; col += 8) {
+        const int grow = (col >> 5) * kD + 32 * (int)crank + (col & 31);
+        const float* src = Whh + (size_t)grow * kD;
+#pragma unroll
+        for (int k = lane; k < kD; k += 32) sW[k * kLstmWPitch + col] = __ldg(src + k);
+    }
+    // initial h (all 256 units of the tile's rows) and c (own 32 units)
+    for (int i = tid; i < kLstmRT * kD; i += 256) {
+        const int r = i >> 8, k = i & 255, n = row0 + r;
+        float v = 0.f;
+        if (n < NC) v = hS[((size_t)ids[n >> 1] * 2 + (n & 1)) * kD + k];
+        sH[i] = v;
+    }
+    for (int i = tid; i < kLstmRT * 32; i += 256) {
+        const int r = i >> 5, u = i & 31, n = row0 + r;
+        float v = 0.f;
+        if (n < NC) v = cS[((size_t)ids[n >> 1] * 2 + (n & 1)) * kD + 32 * crank + u];
+        sC[i] = v;
+    }
+    // every CTA of the cluster is running and initialised before the first DSMEM store
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    const int col = tid & 127, rhalf = tid >> 7;       // thread -> one gate column, 8 of the 16 rows
+    const int gcol = (col >> 5) * kD + 32 * (int)crank + (col & 31);
+    const int cu = tid & 31, cr = tid >> 5;            // cell phase: unit cu, rows cr and cr + 8
+    uint32_t sH_u32 = (uint32_t)__cvta_generic_to_shared(sH);
+    float h_last[2] = {0.f, 0.f};
+
+    for (int t = 0; t < n_steps; ++t) {
+        const float* hcur = sH + (t & 1) * kLstmRT * kD;
+        float gx[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int n = row0 + rhalf * 8 + r;
+            gx[r] = (n < NC) ? __ldg(Gx + ((size_t)n * n_steps + t) * 4 * kD + gcol) : 0.f;
+        }
+        float acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < kD; k += 4) {
+            const float w0 = sW[(k + 0) * kLstmWPitch + col], w1 = sW[(k + 1) * kLstmWPitch + col];
+            const float w2 = sW[(k + 2) * kLstmWPitch + col], w3 = sW[(k + 3) * kLstmWPitch + col];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 hv = *reinterpret_cast<const float4*>(hcur + (rhalf * 8 + r) * kD + k);
+                acc[r] = fmaf(w0, hv.x, acc[r]);
+                acc[r] = fmaf(w1, hv.y, acc[r]);
+                acc[r] = fmaf(w2, hv.z, acc[r]);
+                acc[r] = fmaf(w3, hv.w, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sG[(rhalf * 8 + r) * kLstmGPitch + col] = acc[r] + gx[r];
+        __syncthreads();
+        // cell update for (unit cu, rows cr / cr+8); broadcast the new h to all 8 CTAs of the cluster
+        const uint32_t nxt_off = (uint32_t)(((t + 1) & 1) * kLstmRT * kD) * 4u;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = cr + 8 * rr;
+            const float* gr = sG + r * kLstmGPitch;
+            const float gi = gr[cu], gf = gr[32 + cu], gg = gr[64 + cu], go = gr[96 + cu];
+            const float c = sigmoidf_(gf) * sC[r * 32 + cu] + sigmoidf_(gi) * tanhf(gg);
+            const float h = sigmoidf_(go) * tanhf(c);
+            sC[r * 32 + cu] = c;
+            h_last[rr] = h;
+            const int n = row0 + r;
+            if (n < NC) Y[((size_t)n * n_steps + t) * kD + 32 * crank + cu] = h;
+            const uint32_t local = sH_u32 + nxt_off + (uint32_t)(r * kD + 32 * (int)crank + cu) * 4u;
+#pragma unroll
+            for (unsigned peer = 0; peer < 8; ++peer) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(peer));
+                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(h) : "memory");
+            }
+        }
+        // release our DSMEM stores / acquire the peers' before anyone reads the next h buffer
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    // persist (h, c) of our 32 units
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = cr + 8 * rr, n = row0 + r;
+        if (n < NC) {
+            const size_t o = ((size_t)ids[n >> 1] * 2 + (n & 1)) * kD + 32 * crank + cu;
+            hS[o] = h_last[rr];
+            cS[o] = sC[r * 32 + cu];
+        }
+    }
+}
+
+void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* cS, const int* ids, float* Y, int NC,
+                           int n_steps, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_lstm_recurrent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLstmSmem);
+        attr_set = true;
+    }
+    const int tiles = (NC + kLstmRT - 1) / kLstmRT;
+    k_lstm_recurrent<<<tiles * 8, 256, kLstmSmem, st>>>(Gx, Whh, hS, cS, ids, Y, NC, n_steps);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -501,18 +719,38 @@ void launch_vad(const float* X, const int* tvalid, const float* w, const float* 
 // objective.py:93-110, 186-206; vap_bc_main.py:272-277).  One CTA per stream.
 // Also advances the stream's frame counter (last kernel of the step).
 // -----------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_dot256(const float* __restrict__ wrow, const float* sx, int lane) {
-    float ww[8];
-    load_row8(wrow, lane, ww);
-    float s = 0.f;
+constexpr int kHeadWarps = 16;
+
+// four dot products of 256-wide weight rows with a vector in smem; all weight loads issued up front
+__device__ __forceinline__ void warp_dot256_x4(const float* __restrict__ W, int o0, int n_rows, const float* sx, int lane,
+                                               float (&y)[4]) {
+    float ww[4][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s = fmaf(ww[i], sx[lane * 4 + i], s);
+    for (int q = 0; q < 4; ++q) {
+        const int o = min(o0 + q, n_rows - 1);
+        load_row8(W + (size_t)o * kD, lane, ww[q]);
+    }
+    float xx[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s = fmaf(ww[4 + i], sx[128 + lane * 4 + i], s);
-    return warp_sum(s);
+    for (int i = 0; i < 4; ++i) {
+        xx[i] = sx[lane * 4 + i];
+        xx[4 + i] = sx[128 + lane * 4 + i];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(ww[q][i], xx[i], s);
+        y[q] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[q] += __shfl_xor_sync(0xffffffffu, y[q], o);
+    }
 }
 
-__global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+__global__ void __launch_bounds__(kHeadWarps * 32) k_head(HeadArgs a) {
     __shared__ float sx[2][kD];
     __shared__ float sy[2][kD];
     __shared__ float sh[kD];
@@ -521,15 +759,21 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = a.tvalid[b];
-    sx[0][tid] = a.X[((size_t)(2 * b) * a.T + (t - 1)) * kD + tid];
-    sx[1][tid] = a.X[((size_t)(2 * b + 1) * a.T + (t - 1)) * kD + tid];
+    if (tid < kD) {
+        sx[0][tid] = a.X[((size_t)(2 * b) * a.T + (t - 1)) * kD + tid];
+        sx[1][tid] = a.X[((size_t)(2 * b + 1) * a.T + (t - 1)) * kD + tid];
+    }
     __syncthreads();
-    for (int o = warp; o < kD; o += 8) {
-        const float ya = warp_dot256(a.Wa + (size_t)o * kD, sx[0], lane);
-        const float yb = warp_dot256(a.Wb + (size_t)o * kD, sx[1], lane);
+    for (int o0 = warp * 4; o0 < kD; o0 += kHeadWarps * 4) {
+        float ya[4], yb[4];
+        warp_dot256_x4(a.Wa, o0, kD, sx[0], lane, ya);
+        warp_dot256_x4(a.Wb, o0, kD, sx[1], lane, yb);
         if (lane == 0) {
-            sy[0][o] = ya;
-            sy[1][o] = yb;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sy[0][o0 + q] = ya[q];
+                sy[1][o0 + q] = yb[q];
+            }
         }
     }
     __syncthreads();
@@ -548,38 +792,49 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
         }
     }
     __syncthreads();
-    sh[tid] = sy[0][tid] + sy[1][tid];
-    if (a.comb_tap) a.comb_tap[(size_t)b * kD + tid] = sh[tid];
+    if (tid < kD) {
+        sh[tid] = sy[0][tid] + sy[1][tid];
+        if (a.comb_tap) a.comb_tap[(size_t)b * kD + tid] = sh[tid];
+    }
     __syncthreads();
-    for (int o = warp; o < a.n_out; o += 8) {
-        const float y = warp_dot256(a.Wh + (size_t)o * kD, sh, lane) + a.bh[o];
-        if (lane == 0) sl[o] = y;
+    for (int o0 = warp * 4; o0 < a.n_out; o0 += kHeadWarps * 4) {
+        float y[4];
+        warp_dot256_x4(a.Wh, o0, a.n_out, sh, lane, y);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (o0 + q < a.n_out) sl[o0 + q] = y[q] + a.bh[o0 + q];
+        }
     }
     __syncthreads();
     if (a.logits_tap && tid < a.n_out) a.logits_tap[(size_t)b * kD + tid] = sl[tid];
     float* out = a.out + (size_t)b * 6;
     if (a.head_kind == 0) {
         // softmax over 256 classes, then p[s] = sum_c pi_c * (#active bins of speaker s in the range)
-        float lg = sl[tid];
-        float mx = warp_max(lg);
-        if (lane == 0) red[0][warp] = mx;
+        if (warp < 8) {
+            const float lg = sl[tid];
+            const float mx = warp_max(lg);
+            if (lane == 0) red[0][warp] = mx;
+        }
         __syncthreads();
-        mx = red[0][0];
+        float mx = red[0][0];
 #pragma unroll
         for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[0][i]);
         __syncthreads();
-        const float e = expf(lg - mx);
-        const int c = tid;
-        float vals[5];
-        vals[0] = e;
-        vals[1] = e * (float)(((c >> 0) & 1) + ((c >> 1) & 1));     // now,    speaker 0: bins 0,1
-        vals[2] = e * (float)(((c >> 4) & 1) + ((c >> 5) & 1));     // now,    speaker 1
-        vals[3] = e * (float)(((c >> 2) & 1) + ((c >> 3) & 1));     // future, speaker 0: bins 2,3
-        vals[4] = e * (float)(((c >> 6) & 1) + ((c >> 7) & 1));     // future, speaker 1
+        if (warp < 8) {
+            const float e = expf(sl[tid] - mx);
+            const int c = tid;
+            float vals[5];
+            vals[0] = e;
+            vals[1] = e * (float)(((c >> 0) & 1) + ((c >> 1) & 1));     // now,    speaker 0: bins 0,1
+            vals[2] = e * (float)(((c >> 4) & 1) + ((c >> 5) & 1));     // now,    speaker 1
+            vals[3] = e * (float)(((c >> 2) & 1) + ((c >> 3) & 1));     // future, speaker 0: bins 2,3
+            vals[4] = e * (float)(((c >> 6) & 1) + ((c >> 7) & 1));     // future, speaker 1
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const float s = warp_sum(vals[k]);
-            if (lane == 0) red[k][warp] = s;
+            for (int k = 0; k < 5; ++k) {
+                const float s = warp_sum(vals[k]);
+                if (lane == 0) red[k][warp] = s;
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -613,6 +868,6 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
     }
     if (tid == 0) a.count[a.ids[b]] += 1;
 }
-void launch_head(const HeadArgs& a, cudaStream_t st) { k_head<<<a.B, 256, 0, st>>>(a); }
+void launch_head(const HeadArgs& a, cudaStream_t st) { k_head<<<a.B, kHeadWarps * 32, 0, st>>>(a); }
 
 }  // namespace vapb

@@ -114,7 +114,7 @@ struct vapb_ctx {
     int last_B = 0;
 
     // options
-    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0;
+    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0;
     std::vector<GraphEntry> graphs;
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -390,7 +390,6 @@ void enqueue_step(Step& s) {
         launch_cn_relu(c->act[i + 1], cm, NC * cv.Lout, cv.cnw, cv.cnb, st); mark(s, "cn_relu");
     }
     // ---- LSTM over the inner frames z[:, 1:-1] with persistent (h, c) (encoder.py:76-77)
-    launch_gather_state(c->hS, c->cS, c->ids_dev, c->hW, c->cW, B, st); mark(s, "lstm_state");
     {
         RowMap am;
         am.rpc = c->n_lstm;
@@ -398,18 +397,24 @@ void enqueue_step(Step& s) {
         am.row_stride = kD;
         am.offset = (long long)(c->halo[4] + 1) * kD;
         const RowMap g4 = plain_map(4 * kD);
+        // input projection for all n_lstm frames at once (fp32), then the fused recurrence
         gemm(s, "gemm_lstm_x", c->act[4], am, c->Wih, nullptr, c->b_lstm, nullptr, g4, c->Gx, g4, NC * c->n_lstm, 4 * kD, kD, 0);
-        for (int t = 0; t < c->n_lstm; ++t) {
-            RowMap rm;
-            rm.rpc = 1;
-            rm.chunk_stride = (long long)c->n_lstm * 4 * kD;
-            rm.row_stride = 0;
-            rm.offset = (long long)t * 4 * kD;
-            gemm(s, "gemm_lstm_h", c->hW, plain_map(kD), c->Whh, nullptr, nullptr, c->Gx, rm, c->Gt, g4, NC, 4 * kD, kD, 0);
-            launch_lstm_cell(c->Gt, c->hW, c->cW, c->Y, NC, c->n_lstm, t, st); mark(s, "lstm_cell");
+        if (c->opt_lstm_fused) {
+            launch_lstm_recurrent(c->Gx, c->Whh, c->hS, c->cS, c->ids_dev, c->Y, NC, c->n_lstm, st); mark(s, "lstm_recurrent");
+        } else {
+            launch_gather_state(c->hS, c->cS, c->ids_dev, c->hW, c->cW, B, st); mark(s, "lstm_state");
+            for (int t = 0; t < c->n_lstm; ++t) {
+                RowMap rm;
+                rm.rpc = 1;
+                rm.chunk_stride = (long long)c->n_lstm * 4 * kD;
+                rm.row_stride = 0;
+                rm.offset = (long long)t * 4 * kD;
+                gemm(s, "gemm_lstm_h", c->hW, plain_map(kD), c->Whh, nullptr, nullptr, c->Gx, rm, c->Gt, g4, NC, 4 * kD, kD, 0);
+                launch_lstm_cell(c->Gt, c->hW, c->cW, c->Y, NC, c->n_lstm, t, st); mark(s, "lstm_cell");
+            }
+            launch_scatter_state(c->hS, c->cS, c->ids_dev, c->hW, c->cW, B, st); mark(s, "lstm_state");
         }
     }
-    launch_scatter_state(c->hS, c->cS, c->ids_dev, c->hW, c->cW, B, st); mark(s, "lstm_state");
     // ---- downsample conv over exactly n_lstm frames + LayerNorm + GELU -> ring
     {
         const int Kd = c->n_lstm * kD;
@@ -510,7 +515,14 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     ld.c = c;
     if (!parse_blob(weights_blob, nbytes, ld.t, ld.err)) FAIL_CREATE(VAPB_EWEIGHTS, "%s", ld.err.c_str());
     const std::string G = "encoder.encoder.gEncoder.", A = "encoder.encoder.gAR.baseNet.";
-    c->w0 = ld.up(G + "conv0.weight", {256, 1, 10});
+    {   // conv0 weight [256][1][10] -> tap-major [10][256] so a warp reads it with coalesced float4 loads
+        const HostTensor* h0 = ld.get(G + "conv0.weight", {256, 1, 10});
+        std::vector<float> t(2560, 0.f);
+        if (h0)
+            for (int ch = 0; ch < 256; ++ch)
+                for (int k = 0; k < 10; ++k) t[k * 256 + ch] = h0->data[ch * 10 + k];
+        c->w0 = ld.upload(t);
+    }
     c->b0 = ld.up(G + "conv0.bias", {256});
     c->cn0w = ld.up(G + "batchNorm0.weight", {1, 256, 1});
     c->cn0b = ld.up(G + "batchNorm0.bias", {1, 256, 1});
@@ -811,7 +823,15 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "keep_taps") {
+    else if (k == "lstm_fused" || k == "tile_n") {
+        if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+        h->graphs.clear();
+        if (k == "lstm_fused") h->opt_lstm_fused = value ? 1 : 0;
+        else { h->opt_tile_n = value; h->tcws.force_bn = value; }
+    } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
         if (value && !h->tap_chan) {
             CK(h, cudaSetDevice(h->device));
@@ -833,6 +853,8 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     if (k == "graph") *value = h->opt_graph;
     else if (k == "gemm") *value = h->opt_gemm;
     else if (k == "timing") *value = h->opt_timing;
+    else if (k == "lstm_fused") *value = h->opt_lstm_fused;
+    else if (k == "tile_n") *value = h->opt_tile_n;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
