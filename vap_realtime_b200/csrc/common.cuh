@@ -50,6 +50,10 @@ struct GemmArgs {
     RowMap cmap;
     int M, N, K;
     int act;              // 0 = none, 1 = exact-erf GELU
+    // Optional LayerNorm(256) prologue applied to the rows of A before the product (tcgen05 path,
+    // K == 256 only): A_norm = (A - mean) * rsqrt(var + 1e-5) * ln_w + ln_b  (biased variance).
+    const float* ln_w = nullptr;
+    const float* ln_b = nullptr;
 };
 
 // ---- launchers implemented in kernels_simt.cu -------------------------------------------

@@ -174,7 +174,7 @@ __device__ __forceinline__ void store_a_rows(const float4 (&v)[4][2], uint32_t a
     }
 }
 
-template <int BN>
+template <int BN, bool LN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
     using C = Cfg<BN>;
@@ -223,30 +223,86 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
             const int m = m0 + r0 + 32 * i;
             rowp[i] = (m < g.M) ? (g.A + rowmap_off(g.amap, m) + chunk * 8) : nullptr;
         }
-        // software pipeline: the loads of k-block kb+1 are in flight while kb is split and stored
-        float4 va[4][2], vb[4][2];
-        load_a_rows(rowp, 0, va);
-        for (int kb = 0; kb < nkb; kb += 2) {
-            {
-                const int s = kb % C::kStages;
-                const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
-                if (kb + 1 < nkb) load_a_rows(rowp, kb + 1, vb);
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                store_a_rows(va, a_hi(s), a_lo(s), r0, chunk);
-                fence_proxy_async();                  // generic-proxy smem writes -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(s));
+        // software pipeline over a ring of kPF register buffers: the loads of k-blocks kb+1..kb+kPF-1 are
+        // in flight while kb is split and stored (one L2/HBM round trip is ~1 us, a k-block of MMA far less).
+        // nkb is a multiple of 4 for every K on this path (K in {256, 768, 1024, 1280, 2048}).
+        constexpr int kPF = 4;
+        float4 vr[kPF][4][2];
+        if constexpr (LN) {
+            // LayerNorm prologue (K == 256, nkb == 4): the whole 128 x 256 tile is register resident
+            // (a row = 8 consecutive lanes x 4 k-blocks x 8 floats); two-pass statistics, then the
+            // normalised values are split and stored like any other A tile.
+#pragma unroll
+            for (int j = 0; j < 4; ++j) load_a_rows(rowp, j, vr[j]);
+            float mean[4], rstd[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    sum += (vr[j][i][0].x + vr[j][i][0].y) + (vr[j][i][0].z + vr[j][i][0].w) + (vr[j][i][1].x + vr[j][i][1].y) +
+                           (vr[j][i][1].z + vr[j][i][1].w);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                mean[i] = sum * (1.0f / 256.0f);
+                float sq = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d[8] = {vr[j][i][0].x - mean[i], vr[j][i][0].y - mean[i], vr[j][i][0].z - mean[i],
+                                        vr[j][i][0].w - mean[i], vr[j][i][1].x - mean[i], vr[j][i][1].y - mean[i],
+                                        vr[j][i][1].z - mean[i], vr[j][i][1].w - mean[i]};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) sq = fmaf(d[e], d[e], sq);
+                }
+                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                rstd[i] = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-5f);
             }
-            if (kb + 1 < nkb) {
-                const int s = (kb + 1) % C::kStages;
-                const uint32_t ph = (uint32_t)((kb + 1) / C::kStages) & 1u;
-                if (kb + 2 < nkb) load_a_rows(rowp, kb + 2, va);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.ln_w + j * kBK + chunk * 8));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.ln_w + j * kBK + chunk * 8 + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.ln_b + j * kBK + chunk * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.ln_b + j * kBK + chunk * 8 + 4));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4& a = vr[j][i][0];
+                    float4& b = vr[j][i][1];
+                    a.x = (a.x - mean[i]) * rstd[i] * w0.x + b0.x; a.y = (a.y - mean[i]) * rstd[i] * w0.y + b0.y;
+                    a.z = (a.z - mean[i]) * rstd[i] * w0.z + b0.z; a.w = (a.w - mean[i]) * rstd[i] * w0.w + b0.w;
+                    b.x = (b.x - mean[i]) * rstd[i] * w1.x + b1.x; b.y = (b.y - mean[i]) * rstd[i] * w1.y + b1.y;
+                    b.z = (b.z - mean[i]) * rstd[i] * w1.z + b1.z; b.w = (b.w - mean[i]) * rstd[i] * w1.w + b1.w;
+                }
+                const int s = j % C::kStages;
+                const uint32_t ph = (uint32_t)(j / C::kStages) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
-                store_a_rows(vb, a_hi(s), a_lo(s), r0, chunk);
+                store_a_rows(vr[j], a_hi(s), a_lo(s), r0, chunk);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_bar(s));
             }
+        } else {
+#pragma unroll
+        for (int j = 0; j < kPF - 1; ++j)
+            if (j < nkb) load_a_rows(rowp, j, vr[j]);
+        for (int kb0 = 0; kb0 < nkb; kb0 += kPF) {
+#pragma unroll
+            for (int j = 0; j < kPF; ++j) {
+                const int kb = kb0 + j;
+                if (kb < nkb) {
+                    const int s = kb % C::kStages;
+                    const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
+                    if (kb + kPF - 1 < nkb) load_a_rows(rowp, kb + kPF - 1, vr[(j + kPF - 1) % kPF]);
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    store_a_rows(vr[j], a_hi(s), a_lo(s), r0, chunk);
+                    fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar(s));
+                }
+            }
+        }
         }
         // ================= epilogue =================
         // TMEM lane quadrant = warp % 4 (hardware rule), column half = warp / 4.  Each 32x32 block is
@@ -377,7 +433,9 @@ template <int BN>
 bool ensure_attr(std::string* err) {
     static bool done = false;
     if (done) return true;
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_gemm_tc<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
     if (e != cudaSuccess) {
         if (err) *err = std::string("cudaFuncSetAttribute(k_gemm_tc) failed: ") + cudaGetErrorString(e);
         return false;
@@ -426,28 +484,42 @@ bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vec
 
 bool tc_prepare_workspace(TcWorkspace&, size_t, std::vector<void*>&, std::string&) { return true; }
 
-// Tile width: the widest N tile that still puts a CTA on (nearly) every SM; small problems take narrow tiles.
+// Tile width: one CTA per SM (each CTA takes ~197 KB of shared memory), so the cost of a launch is
+// waves x (fixed cost + work per tile).  Narrow tiles re-read A once per N tile, so ties go to the wider tile.
 int pick_tile(const GemmArgs& g, const TcWeight& w, int force_bn) {
     const int mt = (g.M + kBM - 1) / kBM;
     if (force_bn)
         for (int t = 0; t < 3; ++t)
             if (kTileN[t] == force_bn && w.has_tile[t]) return t;
-    for (int t = 2; t >= 0; --t)
-        if (w.has_tile[t] && mt * (g.N / kTileN[t]) >= 132) return t;
-    for (int t = 0; t < 3; ++t)
-        if (w.has_tile[t]) return t;
-    return 1;
+    int sms = 148;
+    int best = -1;
+    long best_cost = 0;
+    for (int t = 2; t >= 0; --t) {
+        if (!w.has_tile[t]) continue;
+        const long ctas = (long)mt * (g.N / kTileN[t]);
+        const long waves = (ctas + sms - 1) / sms;
+        const long cost = waves * (128 + kTileN[t]);
+        if (best < 0 || cost < best_cost) {
+            best = t;
+            best_cost = cost;
+        }
+    }
+    return best < 0 ? 1 : best;
 }
 
 int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace& ws, cudaStream_t st) {
     const int t = pick_tile(g, w, ws.force_bn);
     dim3 grid((g.M + kBM - 1) / kBM, g.N / kTileN[t]);
-    if (t == 2)
-        k_gemm_tc<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);
-    else if (t == 1)
-        k_gemm_tc<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);
-    else
-        k_gemm_tc<64><<<grid, kThreads, Cfg<64>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);
+    const bool ln = g.ln_w != nullptr && g.K == 256;
+#define VAPB_LAUNCH_TC(BN_)                                                                                         \
+    do {                                                                                                            \
+        if (ln) k_gemm_tc<BN_, true><<<grid, kThreads, Cfg<BN_>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);    \
+        else k_gemm_tc<BN_, false><<<grid, kThreads, Cfg<BN_>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);      \
+    } while (0)
+    if (t == 2) VAPB_LAUNCH_TC(256);
+    else if (t == 1) VAPB_LAUNCH_TC(128);
+    else VAPB_LAUNCH_TC(64);
+#undef VAPB_LAUNCH_TC
     return 1;
 }
 
@@ -457,15 +529,17 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
     const int tsel = variant / 16;
     variant %= 16;
     const int force_bn = tsel == 0 ? 0 : kTileN[tsel - 1];
-    struct Case { int M, N, K; int conv; int bias, act, resid; };
+    struct Case { int M, N, K; int conv; int bias, act, resid; int ln; };
     // conv: A is a channels-last chunked view with overlapping rows (conv1 geometry: k=8, s=4, pad=2, L 224 -> 56)
     static const Case cases[] = {
-        {300, 256, 256, 0, 0, 0, 0},
-        {1000, 768, 256, 0, 1, 1, 0},
-        {7 * 56, 256, 2048, 1, 1, 0, 0},
-        {640, 512, 768, 0, 0, 0, 1},
-        {129, 256, 1280, 0, 1, 0, 1},
-        {6400, 256, 768, 0, 0, 0, 1},
+        {300, 256, 256, 0, 0, 0, 0, 0},
+        {1000, 768, 256, 0, 1, 1, 0, 0},
+        {7 * 56, 256, 2048, 1, 1, 0, 0, 0},
+        {640, 512, 768, 0, 0, 0, 1, 0},
+        {129, 256, 1280, 0, 1, 0, 1, 0},
+        {6400, 256, 768, 0, 0, 0, 1, 0},
+        {900, 768, 256, 0, 0, 1, 0, 1},      // LayerNorm prologue + GELU (the FFN1 shape)
+        {333, 256, 256, 0, 0, 0, 1, 1},      // LayerNorm prologue + residual
     };
     const int ncases = (int)(sizeof(cases) / sizeof(cases[0]));
     if (variant < 0 || variant >= ncases) {
@@ -522,7 +596,19 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
         GemmArgs g;
         g.A = dA; g.amap = amap; g.W = dW; g.bias = cs.bias ? db : nullptr; g.R = cs.resid ? dR : nullptr;
         g.rmap = plain_map(N); g.C = dC0; g.cmap = plain_map(N); g.M = M; g.N = N; g.K = K; g.act = cs.act;
-        launch_sgemm(g, 0);
+        if (cs.ln) {
+            // reference: stand-alone LayerNorm kernel, then the fp32 GEMM (ln affine = first 256 of hb / hR)
+            float* dZ;
+            al(&dZ, a_elems);
+            launch_layernorm(dA, amap, dZ, amap, M, db, dR, 0, 0);
+            g.A = dZ;
+            launch_sgemm(g, 0);
+            g.A = dA;
+            g.ln_w = db;
+            g.ln_b = dR;
+        } else {
+            launch_sgemm(g, 0);
+        }
         g.C = dC1;
         TcWorkspace ws;
         ws.force_bn = force_bn;

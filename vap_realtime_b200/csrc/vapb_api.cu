@@ -114,7 +114,7 @@ struct vapb_ctx {
     int last_B = 0;
 
     // options
-    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0;
+    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1;
     std::vector<GraphEntry> graphs;
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -318,8 +318,10 @@ void mark(Step& s, const char* tag, int launches = 1) {
 
 // C = act(A W^T + bias) + R through the selected GEMM engine.
 void gemm(Step& s, const char* tag, const float* A, RowMap amap, const float* W, const TcWeight* tcw, const float* bias,
-          const float* R, RowMap rmap, float* C, RowMap cmap, int M, int N, int K, int act) {
+          const float* R, RowMap rmap, float* C, RowMap cmap, int M, int N, int K, int act, const float* ln_w = nullptr,
+          const float* ln_b = nullptr) {
     GemmArgs g;
+    g.ln_w = ln_w; g.ln_b = ln_b;
     g.A = A; g.amap = amap; g.W = W; g.bias = bias; g.R = R; g.rmap = rmap; g.C = C; g.cmap = cmap;
     g.M = M; g.N = N; g.K = K; g.act = act;
     if (s.c->opt_gemm == 1 && tcw && tcw->hi) {
@@ -353,19 +355,33 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
         gemm(s, "gemm_kv_cross", c->X, pd, lw.Wkv_c, &lw.tc_kv_c, nullptr, nullptr, pd, c->KVc, p2, R, 2 * kD, kD, 0);
     }
     // self attention block (modules.py:268-272)
-    launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_sa_w, lw.ln_sa_b, 0, s.st); mark(s, "layernorm");
-    gemm(s, "gemm_qkv", c->Z, pd, lw.sa.Wqkv, &lw.sa.tc_qkv, nullptr, nullptr, pd, c->QKV, p3, R, 3 * kD, kD, 0);
+    // LayerNorm is a prologue of the consuming GEMM on the tensor-core path, a kernel of its own otherwise
+    const bool fuse_ln = c->opt_gemm == 1 && c->opt_fuse_ln;
+    if (fuse_ln) {
+        gemm(s, "gemm_ln_qkv", c->X, pd, lw.sa.Wqkv, &lw.sa.tc_qkv, nullptr, nullptr, pd, c->QKV, p3, R, 3 * kD, kD, 0, lw.ln_sa_w, lw.ln_sa_b);
+    } else {
+        launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_sa_w, lw.ln_sa_b, 0, s.st); mark(s, "layernorm");
+        gemm(s, "gemm_qkv", c->Z, pd, lw.sa.Wqkv, &lw.sa.tc_qkv, nullptr, nullptr, pd, c->QKV, p3, R, 3 * kD, kD, 0);
+    }
     attention(s, c->QKV, 3 * kD, c->QKV + kD, 3 * kD, c->QKV + 2 * kD, 3 * kD, c->O, lw.sa.slopes, 0);
     gemm(s, "gemm_proj", c->O, pd, lw.sa.Wproj, &lw.sa.tc_proj, nullptr, c->X, pd, c->X, pd, R, kD, kD, 0);
     if (lw.cross) {
-        launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_src_w, lw.ln_src_b, 0, s.st); mark(s, "layernorm");
-        gemm(s, "gemm_q_cross", c->Z, pd, lw.Wq_c, &lw.tc_q_c, nullptr, nullptr, pd, c->Qc, pd, R, kD, kD, 0);
+        if (fuse_ln) {
+            gemm(s, "gemm_ln_q_cross", c->X, pd, lw.Wq_c, &lw.tc_q_c, nullptr, nullptr, pd, c->Qc, pd, R, kD, kD, 0, lw.ln_src_w, lw.ln_src_b);
+        } else {
+            launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_src_w, lw.ln_src_b, 0, s.st); mark(s, "layernorm");
+            gemm(s, "gemm_q_cross", c->Z, pd, lw.Wq_c, &lw.tc_q_c, nullptr, nullptr, pd, c->Qc, pd, R, kD, kD, 0);
+        }
         attention(s, c->Qc, kD, c->KVc, 2 * kD, c->KVc + kD, 2 * kD, c->O, lw.slopes_c, 1);
         gemm(s, "gemm_proj", c->O, pd, lw.Wproj_c, &lw.tc_proj_c, nullptr, c->X, pd, c->X, pd, R, kD, kD, 0);
     }
     // feed forward (modules.py:9-21, 285): Linear(256,768) -> GELU -> Linear(768,256), no biases
-    launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_ff_w, lw.ln_ff_b, 0, s.st); mark(s, "layernorm");
-    gemm(s, "gemm_ffn1", c->Z, pd, lw.W1, &lw.tc_w1, nullptr, nullptr, pd, c->Hd, pf, R, kFF, kD, 1);
+    if (fuse_ln) {
+        gemm(s, "gemm_ln_ffn1", c->X, pd, lw.W1, &lw.tc_w1, nullptr, nullptr, pd, c->Hd, pf, R, kFF, kD, 1, lw.ln_ff_w, lw.ln_ff_b);
+    } else {
+        launch_layernorm(c->X, pd, c->Z, pd, R, lw.ln_ff_w, lw.ln_ff_b, 0, s.st); mark(s, "layernorm");
+        gemm(s, "gemm_ffn1", c->Z, pd, lw.W1, &lw.tc_w1, nullptr, nullptr, pd, c->Hd, pf, R, kFF, kD, 1);
+    }
     gemm(s, "gemm_ffn2", c->Hd, pf, lw.W2, &lw.tc_w2, nullptr, c->X, pd, c->X, pd, R, kD, kFF, 0);
 }
 
@@ -823,13 +839,14 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
         for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
         h->graphs.clear();
         if (k == "lstm_fused") h->opt_lstm_fused = value ? 1 : 0;
+        else if (k == "fuse_ln") h->opt_fuse_ln = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -855,6 +872,7 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "timing") *value = h->opt_timing;
     else if (k == "lstm_fused") *value = h->opt_lstm_fused;
     else if (k == "tile_n") *value = h->opt_tile_n;
+    else if (k == "fuse_ln") *value = h->opt_fuse_ln;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
