@@ -54,6 +54,7 @@ struct GemmArgs {
     // K == 256 only): A_norm = (A - mean) * rsqrt(var + 1e-5) * ln_w + ln_b  (biased variance).
     const float* ln_w = nullptr;
     const float* ln_b = nullptr;
+    long long* dbg = nullptr;     // optional: 8 clock64 stamps per CTA (self-test / tuning only)
 };
 
 // ---- launchers implemented in kernels_simt.cu -------------------------------------------

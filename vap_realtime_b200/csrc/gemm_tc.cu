@@ -212,6 +212,8 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    long long* dbg = g.dbg ? g.dbg + 8 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    if (dbg && tid == 0) dbg[0] = clock64();
 
     if (warp < kProducerWarps) {
         // ================= A producers =================
@@ -304,6 +306,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
             }
         }
         }
+        if (dbg && tid == 0) dbg[1] = clock64();          // all A tiles produced
         // ================= epilogue =================
         // TMEM lane quadrant = warp % 4 (hardware rule), column half = warp / 4.  Each 32x32 block is
         // transposed through a private smem buffer so that global reads/writes are 128-byte coalesced.
@@ -320,6 +323,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
         float* tbuf = reinterpret_cast<float*>(base_ptr) + warp * (32 * kEpiPitch);
         mbar_wait(bar_accum, 0);
         tc_fence_after();
+        if (dbg && tid == 0) dbg[2] = clock64();          // accumulator complete, epilogue starts
 #pragma unroll 1
         for (int cb = 0; cb < kChunks; ++cb) {
             const int col0 = half * (BN / 2) + cb * 32;
@@ -343,6 +347,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
             }
             __syncwarp();
         }
+        if (dbg && tid == 0) dbg[3] = clock64();          // epilogue of warp 0 done
     } else if (warp == kProducerWarps) {
         // ================= TMA producer (W planes) =================
         if (lane == 0) {
@@ -354,6 +359,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                 tma_load_2d(w_hi(s), &map_hi, kb * kBK, n0, full_bar(s));
                 tma_load_2d(w_lo(s), &map_lo, kb * kBK, n0, full_bar(s));
             }
+            if (dbg) dbg[6] = clock64();              // last TMA issued
         }
     } else {
         // ================= MMA issuer =================
@@ -364,6 +370,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                 const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
                 mbar_wait(full_bar(s), ph);
                 tc_fence_after();
+                if (dbg && kb == 0) dbg[4] = clock64();   // first stage full
 #pragma unroll
                 for (int k = 0; k < kBK / kUmmaK; ++k) {
                     const uint32_t koff = (uint32_t)k * kUmmaK * 2;          // bytes along K inside the swizzle row
@@ -376,6 +383,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                 umma_commit(empty_bar(s));            // frees the stage when these MMAs have read it
             }
             umma_commit(bar_accum);                   // accumulator complete
+            if (dbg) dbg[5] = clock64();              // last MMA issued
         }
     }
     tc_fence_before();
@@ -540,6 +548,12 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
         {6400, 256, 768, 0, 0, 0, 1, 0},
         {900, 768, 256, 0, 0, 1, 0, 1},      // LayerNorm prologue + GELU (the FFN1 shape)
         {333, 256, 256, 0, 0, 0, 1, 1},      // LayerNorm prologue + residual
+        {6400, 256, 256, 0, 0, 0, 1, 0},     // 8: proj shape at B=64 (residual)
+        {6400, 256, 256, 0, 0, 0, 0, 0},     // 9: same, no residual
+        {6400, 768, 256, 0, 0, 1, 0, 1},     // 10: LN + FFN1 shape
+        {6400, 768, 256, 0, 0, 0, 0, 0},     // 11: QKV shape, no LN
+        {128 * 56, 256, 2048, 1, 1, 0, 0, 0},// 12: conv1 at B=64
+        {128, 256, 1280, 0, 1, 0, 0, 0},     // 13: downsample at B=64
     };
     const int ncases = (int)(sizeof(cases) / sizeof(cases[0]));
     if (variant < 0 || variant >= ncases) {
@@ -586,7 +600,7 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
     cudaMemset(dC0, 0, hR.size() * 4);
     cudaMemset(dC1, 0xFF, hR.size() * 4);
     TcWeight tw;
-    std::string err;
+    std::string err, timing_note;
     int rc = 0;
     if (!tc_prepare_weight(dW, N, K, tw, allocs, err)) {
         report = err;
@@ -614,6 +628,35 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
         ws.force_bn = force_bn;
         launch_gemm_tc(g, tw, ws, 0);
         cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) {
+            // timing (L2-warm, 20 back-to-back launches) + clock64 phase stamps of CTA (0,0)
+            long long* ddbg = nullptr;
+            const size_t nct = (size_t)((M + 127) / 128) * (N / 64);
+            cudaMalloc(reinterpret_cast<void**>(&ddbg), nct * 8 * sizeof(long long));
+            allocs.push_back(ddbg);
+            cudaMemset(ddbg, 0, nct * 8 * sizeof(long long));
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, 0);
+            for (int it = 0; it < 20; ++it) launch_gemm_tc(g, tw, ws, 0);
+            cudaEventRecord(e1, 0);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            g.dbg = ddbg;
+            launch_gemm_tc(g, tw, ws, 0);
+            g.dbg = nullptr;
+            e = cudaDeviceSynchronize();
+            long long st[8];
+            cudaMemcpy(st, ddbg, sizeof st, cudaMemcpyDeviceToHost);
+            char tb[256];
+            snprintf(tb, sizeof tb, " | %.2f us/launch warm; CTA0 cycles: produced %lld, first_full %lld, last_mma_issue %lld, last_tma %lld, accum_ready %lld, epi_done %lld",
+                     ms * 1000.f / 20.f, st[1] - st[0], st[4] - st[0], st[5] - st[0], st[6] - st[0], st[2] - st[0], st[3] - st[0]);
+            timing_note = tb;
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
         if (e != cudaSuccess) {
             report = std::string("kernel failed: ") + cudaGetErrorString(e);
             rc = -4;
@@ -639,7 +682,7 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
                  "C[0][0..3] ref=%.5g %.5g %.5g %.5g tc=%.5g %.5g %.5g %.5g",
                  variant, M, N, K, force_bn, maxabs, maxdiff, *max_rel_err, nbad, worst / N, worst % N, c0[worst], c1[worst],
                  c0[0], c0[1], c0[2], c0[3], c1[0], c1[1], c1[2], c1[3]);
-        report = buf;
+        report = std::string(buf) + timing_note;
     }
     for (void* p : allocs) cudaFree(p);
     return rc;
