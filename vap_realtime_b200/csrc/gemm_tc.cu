@@ -24,7 +24,7 @@ constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
 constexpr int kProducerWarps = 8; // A producers, afterwards the epilogue
 constexpr int kThreads = (kProducerWarps + 2) * 32;   // + TMA warp + MMA warp
 constexpr int kATile = kBM * kBK * 2;     // bytes per A plane per stage (16 KB)
-constexpr int kEpiPitch = 33;             // floats per row of the per-warp epilogue transpose buffer
+constexpr int kEpiPitch = 36;             // floats per row of the per-warp epilogue transpose buffer (16 B aligned rows)
 
 template <int BN>
 struct Cfg {
@@ -174,6 +174,56 @@ __device__ __forceinline__ void store_a_rows(const float4 (&v)[4][2], uint32_t a
     }
 }
 
+// Epilogue of one warp: kChunks blocks of 32 rows x 32 columns.  The thread-per-row TMEM read-out is
+// transposed through a private smem buffer (pitch 36 floats, 128-bit accesses) so that every global
+// access is a float4 with 8 lanes covering 128 contiguous bytes of one row.  All residual loads of a
+// block are in flight before the first one is consumed.
+template <int kChunks, bool HAS_R, bool GELU>
+__device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tm_row, float* tbuf, int n_base, int tm_col0,
+                                                int lane, int rows_valid, long long coff_own, long long roff_own) {
+    const int sub = lane >> 3;        // row within a group of 4
+    const int c4 = (lane & 7) * 4;    // first of this lane's 4 columns
+#pragma unroll 1
+    for (int cb = 0; cb < kChunks; ++cb) {
+        uint32_t raw[32];
+        tmem_ld32(tm_row + (uint32_t)(tm_col0 + cb * 32), raw);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(tbuf + lane * kEpiPitch + 4 * q) =
+                make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                            __uint_as_float(raw[4 * q + 3]));
+        __syncwarp();
+        const int n = n_base + cb * 32 + c4;
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias) bias = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        long long coff[8];
+        float4 res[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = 4 * it + sub;
+            coff[it] = __shfl_sync(0xffffffffu, coff_own, rr);
+            if (HAS_R) {
+                const long long roff = __shfl_sync(0xffffffffu, roff_own, rr);
+                res[it] = (rr < rows_valid) ? *reinterpret_cast<const float4*>(g.R + roff + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = 4 * it + sub;
+            float4 x = *reinterpret_cast<const float4*>(tbuf + rr * kEpiPitch + c4);
+            x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
+            if (GELU) {
+                x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+            }
+            if (HAS_R) {
+                x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
+            }
+            if (rr < rows_valid) *reinterpret_cast<float4*>(g.C + coff[it] + n) = x;
+        }
+        __syncwarp();
+    }
+}
+
 template <int BN, bool LN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
@@ -312,8 +362,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
         // transposed through a private smem buffer so that global reads/writes are 128-byte coalesced.
         const int quad = warp & 3, half = warp >> 2;
         constexpr int kChunks = BN / 64;               // 32-column chunks per warp
-        const int row_l = quad * 32 + lane;            // accumulator row owned by this thread (TMEM lane)
-        const int m_own = m0 + row_l;
+        const int m_own = m0 + quad * 32 + lane;       // accumulator row owned by this thread (TMEM lane)
         long long coff_own = 0, roff_own = 0;
         if (m_own < g.M) {
             coff_own = rowmap_off(g.cmap, m_own);
@@ -324,28 +373,13 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
         mbar_wait(bar_accum, 0);
         tc_fence_after();
         if (dbg && tid == 0) dbg[2] = clock64();          // accumulator complete, epilogue starts
-#pragma unroll 1
-        for (int cb = 0; cb < kChunks; ++cb) {
-            const int col0 = half * (BN / 2) + cb * 32;
-            uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, raw);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) tbuf[lane * kEpiPitch + c] = __uint_as_float(raw[c]);
-            __syncwarp();
-            const int n = n0 + col0 + lane;
-            const float bias = g.bias ? __ldg(g.bias + n) : 0.f;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-                const long long coff = __shfl_sync(0xffffffffu, coff_own, rr);
-                const long long roff = __shfl_sync(0xffffffffu, roff_own, rr);
-                if (rr < rows_valid) {
-                    float x = tbuf[rr * kEpiPitch + lane] + bias;
-                    if (g.act == 1) x = gelu_erf(x);
-                    if (g.R) x += g.R[roff + n];
-                    g.C[coff + n] = x;
-                }
-            }
-            __syncwarp();
+        const uint32_t tm_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        if (g.R) {
+            if (g.act == 1) epilogue_chunks<kChunks, true, true>(g, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+            else epilogue_chunks<kChunks, true, false>(g, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+        } else {
+            if (g.act == 1) epilogue_chunks<kChunks, false, true>(g, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+            else epilogue_chunks<kChunks, false, false>(g, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
         }
         if (dbg && tid == 0) dbg[3] = clock64();          // epilogue of warp 0 done
     } else if (warp == kProducerWarps) {
