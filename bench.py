@@ -129,8 +129,8 @@ def cpu_step_rate(B: int, T: int, head: str, steps: int, warmup: int, threads=No
     at steady state (window full).  Returns (frames/s, seconds per step list)."""
     import torch
     from oracle.vap_oracle import OracleState, VapOracle
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     w, _ = load_weights(head)
     o = VapOracle(w, FRAME_HZ, T, head)
     st = OracleState(B)
@@ -157,6 +157,7 @@ def run_reference(args):
         return 0
     import torch
     B, T = args.batch_per_gpu * 1, args.ctx_frames       # same per-step workload as our arm at N=1
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
     cores = torch.get_num_threads()
     # bounded sample: if K full-batch steps would not finish within ~2 minutes, each step times 16 of the B streams
     _, probe = cpu_step_rate(B, T, args.head, 1, 1)
@@ -203,6 +204,10 @@ def run_ours(args):
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NCCL prints its version banner to stdout when NCCL_DEBUG is set; keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -235,6 +240,9 @@ def run_ours(args):
         step_i += 1
     torch.cuda.synchronize()
     launches_per_step = eng.last_launch_count
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
 
     # ---- device-resident timing: per-step events, L2 flushed between steps
     sampler = ClockSampler(local)
@@ -333,6 +341,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             import torch as _t
+            _t.set_num_threads(len(os.sched_getaffinity(0)))
             cores = _t.get_num_threads()
             bfps, _ = cpu_step_rate(B, T, args.head, steps=args.cpu_steps, warmup=1)
             sfps, _ = cpu_step_rate(1, T, args.head, steps=100, warmup=5)

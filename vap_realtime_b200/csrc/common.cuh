@@ -57,6 +57,32 @@ struct GemmArgs {
     long long* dbg = nullptr;     // optional: 8 clock64 stamps per CTA (self-test / tuning only)
 };
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// Every kernel of the step calls pdl_trigger() first (lets the NEXT kernel of the stream start its
+// prologue: barrier init, TMEM allocation, tensor-map prefetch, weight TMA) and pdl_wait() before it
+// touches anything a previous kernel produced.  Both are no-ops for a normal launch.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern bool g_use_pdl;      // set by the step driver before it enqueues kernels
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- launchers implemented in kernels_simt.cu -------------------------------------------
 void launch_conv0(const float* audio, int n_chunks, int S, int L0, const float* w, const float* b,
                   const float* cnw, const float* cnb, float* out, RowMap omap, cudaStream_t st);

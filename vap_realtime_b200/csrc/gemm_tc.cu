@@ -134,12 +134,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi); two elements per packed conversion
+// (cvt.rn.bf16x2.f32 d, a, b puts a in the upper and b in the lower half of d).
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    uint32_t h, l;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - h1), "f"(x0 - h0));
+    hi = h;
+    lo = l;
 }
 
 // ---- the kernel -----------------------------------------------------------------------
@@ -228,6 +231,7 @@ template <int BN, bool LN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
     using C = Cfg<BN>;
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -267,6 +271,8 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
 
     if (warp < kProducerWarps) {
         // ================= A producers =================
+        pdl_wait();                                    // A (and later the residual) come from earlier kernels;
+                                                       // the W planes fetched by the TMA warp are constants
         const int chunk = tid & 7;                     // 16-byte chunk (8 bf16) within the 128-byte row
         const int r0 = tid >> 3;                       // rows r0 + 32*i
         const float* rowp[4];
@@ -425,6 +431,198 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     if (warp == kProducerWarps + 1) tmem_dealloc(tmem_base, BN);
 }
 
+// ---- K = 256 kernel: A resident in shared memory, loop over N ------------------------------------
+// Most GEMMs of the transformer have K = 256 (QKV, Q/KV of the cross attention, the projections,
+// FFN1).  Here a CTA converts its 128 x 256 A tile ONCE (optionally through the LayerNorm prologue),
+// keeps both bf16 planes resident (128 KB) and walks over `ns` 64-wide N subtiles, streaming only the
+// W planes through a 3-deep TMA ring.  Every subtile has its own TMEM columns, so the epilogue of
+// subtile i overlaps the MMAs of subtile i+1, and the A conversion is not repeated per N tile.
+constexpr int kR_WStages = 3;
+constexpr int kR_WTile = 64 * kBK * 2;                      // one W plane of a 64-row subtile: 8 KB
+constexpr int kR_ABytes = 4 * 2 * kATile;                   // 4 k-blocks x (hi + lo) = 128 KB
+constexpr int kR_EpiBytes = kProducerWarps * 32 * kEpiPitch * 4;
+constexpr int kR_SmemBytes = kR_ABytes + kR_WStages * 2 * kR_WTile + kR_EpiBytes + 1024 + 256;
+constexpr int kR_MaxSub = 8;                                // 8 x 64 = 512 TMEM columns
+
+template <bool LN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_tc_k256(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+               int ns /* 64-wide subtiles per CTA */, int tmem_cols) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    auto a_hi = [&](int kb) { return base + (uint32_t)kb * 2 * kATile; };
+    auto a_lo = [&](int kb) { return a_hi(kb) + kATile; };
+    const uint32_t wbase = base + kR_ABytes;
+    auto w_hi = [&](int s) { return wbase + (uint32_t)s * 2 * kR_WTile; };
+    auto w_lo = [&](int s) { return w_hi(s) + kR_WTile; };
+    float* epi = reinterpret_cast<float*>(base_ptr + kR_ABytes + kR_WStages * 2 * kR_WTile);
+    const uint32_t bars = wbase + kR_WStages * 2 * kR_WTile + kR_EpiBytes;
+    auto a_full = [&](int kb) { return bars + 8u * kb; };                        // 4
+    auto w_full = [&](int s) { return bars + 32u + 8u * s; };                    // 3
+    auto w_empty = [&](int s) { return bars + 56u + 8u * s; };                   // 3
+    auto acc_full = [&](int st) { return bars + 80u + 8u * st; };                // 8
+    const uint32_t tmem_slot = bars + 144u;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * kBM;
+    const int n_begin = blockIdx.y * ns * 64;
+
+    if (warp == kProducerWarps && lane == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(a_full(i), kProducerWarps);
+        for (int i = 0; i < kR_WStages; ++i) {
+            mbar_init(w_full(i), 1);
+            mbar_init(w_empty(i), 1);
+        }
+        for (int i = 0; i < kR_MaxSub; ++i) mbar_init(acc_full(i), 1);
+        fence_barrier_init();
+        prefetch_tmap(&map_hi);
+        prefetch_tmap(&map_lo);
+    }
+    if (warp == kProducerWarps + 1) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp < kProducerWarps) {
+        // ================= A producers: the whole 128 x 256 tile, once =================
+        pdl_wait();
+        const int chunk = tid & 7;
+        const int r0 = tid >> 3;
+        const float* rowp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + r0 + 32 * i;
+            rowp[i] = (m < g.M) ? (g.A + rowmap_off(g.amap, m) + chunk * 8) : nullptr;
+        }
+        float4 vr[4][4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load_a_rows(rowp, j, vr[j]);
+        float mean[4], rstd[4];
+        if constexpr (LN) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    sum += (vr[j][i][0].x + vr[j][i][0].y) + (vr[j][i][0].z + vr[j][i][0].w) + (vr[j][i][1].x + vr[j][i][1].y) +
+                           (vr[j][i][1].z + vr[j][i][1].w);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                mean[i] = sum * (1.0f / 256.0f);
+                float sq = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d[8] = {vr[j][i][0].x - mean[i], vr[j][i][0].y - mean[i], vr[j][i][0].z - mean[i],
+                                        vr[j][i][0].w - mean[i], vr[j][i][1].x - mean[i], vr[j][i][1].y - mean[i],
+                                        vr[j][i][1].z - mean[i], vr[j][i][1].w - mean[i]};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) sq = fmaf(d[e], d[e], sq);
+                }
+                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                rstd[i] = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-5f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if constexpr (LN) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.ln_w + j * kBK + chunk * 8));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.ln_w + j * kBK + chunk * 8 + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.ln_b + j * kBK + chunk * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.ln_b + j * kBK + chunk * 8 + 4));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4& a = vr[j][i][0];
+                    float4& b = vr[j][i][1];
+                    a.x = (a.x - mean[i]) * rstd[i] * w0.x + b0.x; a.y = (a.y - mean[i]) * rstd[i] * w0.y + b0.y;
+                    a.z = (a.z - mean[i]) * rstd[i] * w0.z + b0.z; a.w = (a.w - mean[i]) * rstd[i] * w0.w + b0.w;
+                    b.x = (b.x - mean[i]) * rstd[i] * w1.x + b1.x; b.y = (b.y - mean[i]) * rstd[i] * w1.y + b1.y;
+                    b.z = (b.z - mean[i]) * rstd[i] * w1.z + b1.z; b.w = (b.w - mean[i]) * rstd[i] * w1.w + b1.w;
+                }
+            }
+            store_a_rows(vr[j], a_hi(j), a_lo(j), r0, chunk);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(j));
+        }
+        // ================= epilogue: one 32 x 32 block per warp and subtile =================
+        const int quad = warp & 3, half = warp >> 2;
+        const int m_own = m0 + quad * 32 + lane;
+        long long coff_own = 0, roff_own = 0;
+        if (m_own < g.M) {
+            coff_own = rowmap_off(g.cmap, m_own);
+            if (g.R) roff_own = rowmap_off(g.rmap, m_own);
+        }
+        const int rows_valid = min(32, g.M - (m0 + quad * 32));
+        float* tbuf = epi + warp * (32 * kEpiPitch);
+        const uint32_t tm_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int st = 0; st < ns; ++st) {
+            mbar_wait(acc_full(st), 0);
+            tc_fence_after();
+            const int ncol = n_begin + st * 64 + half * 32;
+            const int tcol = st * 64 + half * 32;
+            if (g.R) {
+                if (g.act == 1) epilogue_chunks<1, true, true>(g, tm_row, tbuf, ncol, tcol, lane, rows_valid, coff_own, roff_own);
+                else epilogue_chunks<1, true, false>(g, tm_row, tbuf, ncol, tcol, lane, rows_valid, coff_own, roff_own);
+            } else {
+                if (g.act == 1) epilogue_chunks<1, false, true>(g, tm_row, tbuf, ncol, tcol, lane, rows_valid, coff_own, roff_own);
+                else epilogue_chunks<1, false, false>(g, tm_row, tbuf, ncol, tcol, lane, rows_valid, coff_own, roff_own);
+            }
+        }
+    } else if (warp == kProducerWarps) {
+        // ================= TMA producer: W planes of every (subtile, k-block) =================
+        if (lane == 0) {
+            int it = 0;
+            for (int st = 0; st < ns; ++st) {
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % kR_WStages;
+                    const uint32_t ph = (uint32_t)(it / kR_WStages) & 1u;
+                    mbar_wait(w_empty(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(w_full(s), 2u * kR_WTile);
+                    tma_load_2d(w_hi(s), &map_hi, kb * kBK, n_begin + st * 64, w_full(s));
+                    tma_load_2d(w_lo(s), &map_lo, kb * kBK, n_begin + st * 64, w_full(s));
+                }
+            }
+        }
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(64);
+            int it = 0;
+            for (int st = 0; st < ns; ++st) {
+                const uint32_t tm_acc = tmem_base + (uint32_t)(st * 64);
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % kR_WStages;
+                    const uint32_t ph = (uint32_t)(it / kR_WStages) & 1u;
+                    if (st == 0) mbar_wait(a_full(kb), 0);
+                    mbar_wait(w_full(s), ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t koff = (uint32_t)k * kUmmaK * 2;
+                        const uint64_t ah = make_desc(a_hi(kb) + koff), al = make_desc(a_lo(kb) + koff);
+                        const uint64_t wh = make_desc(w_hi(s) + koff), wl = make_desc(w_lo(s) + koff);
+                        umma_bf16(tm_acc, al, wh, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tm_acc, ah, wl, idesc, 1u);
+                        umma_bf16(tm_acc, ah, wh, idesc, 1u);
+                    }
+                    umma_commit(w_empty(s));
+                }
+                umma_commit(acc_full(st));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProducerWarps + 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
 // fp32 [n] -> bf16 hi / lo planes
 __global__ void k_split_planes(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -521,6 +719,16 @@ bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vec
         if (!encode_plane(&out.map_lo[t], lo, N, K, kTileN[t], err)) return false;
     }
     if (!ensure_attr<64>(&err) || !ensure_attr<128>(&err) || !ensure_attr<256>(&err)) return false;
+    static bool k256_done = false;
+    if (!k256_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc_k256<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc_k256<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
+        if (e != cudaSuccess) {
+            err = std::string("cudaFuncSetAttribute(k_gemm_tc_k256) failed: ") + cudaGetErrorString(e);
+            return false;
+        }
+        k256_done = true;
+    }
     return true;
 }
 
@@ -549,14 +757,39 @@ int pick_tile(const GemmArgs& g, const TcWeight& w, int force_bn) {
     return best < 0 ? 1 : best;
 }
 
+// Resident-A path: number of N splits (grid.y) for the K = 256 kernel, 0 if it does not apply.
+int pick_k256_split(const GemmArgs& g) {
+    if (g.K != 256 || g.N % 64 != 0) return 0;
+    const int nsub = g.N / 64, mt = (g.M + kBM - 1) / kBM;
+    int best = 0;
+    for (int split = 1; split <= nsub; ++split) {
+        if (nsub % split != 0 || nsub / split > kR_MaxSub) continue;
+        if (best == 0) best = split;                    // smallest legal split (least A re-conversion)
+        if (mt * split <= 148) best = split;            // ... but use idle SMs while one wave still suffices
+    }
+    return best;
+}
+
 int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace& ws, cudaStream_t st) {
+    if (ws.use_k256 && ws.force_bn == 0) {
+        const int split = pick_k256_split(g);
+        if (split > 0 && w.has_tile[0]) {
+            const int ns = g.N / 64 / split;
+            int cols = 32;
+            while (cols < ns * 64) cols *= 2;
+            dim3 grid((g.M + kBM - 1) / kBM, split);
+            if (g.ln_w) launch_k(k_gemm_tc_k256<true>, grid, dim3(kThreads), kR_SmemBytes, st, g, w.map_hi[0], w.map_lo[0], ns, cols);
+            else launch_k(k_gemm_tc_k256<false>, grid, dim3(kThreads), kR_SmemBytes, st, g, w.map_hi[0], w.map_lo[0], ns, cols);
+            return 1;
+        }
+    }
     const int t = pick_tile(g, w, ws.force_bn);
     dim3 grid((g.M + kBM - 1) / kBM, g.N / kTileN[t]);
     const bool ln = g.ln_w != nullptr && g.K == 256;
 #define VAPB_LAUNCH_TC(BN_)                                                                                         \
     do {                                                                                                            \
-        if (ln) k_gemm_tc<BN_, true><<<grid, kThreads, Cfg<BN_>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);    \
-        else k_gemm_tc<BN_, false><<<grid, kThreads, Cfg<BN_>::kSmemBytes, st>>>(g, w.map_hi[t], w.map_lo[t]);      \
+        if (ln) launch_k(k_gemm_tc<BN_, true>, grid, dim3(kThreads), Cfg<BN_>::kSmemBytes, st, g, w.map_hi[t], w.map_lo[t]);    \
+        else launch_k(k_gemm_tc<BN_, false>, grid, dim3(kThreads), Cfg<BN_>::kSmemBytes, st, g, w.map_hi[t], w.map_lo[t]);      \
     } while (0)
     if (t == 2) VAPB_LAUNCH_TC(256);
     else if (t == 1) VAPB_LAUNCH_TC(128);

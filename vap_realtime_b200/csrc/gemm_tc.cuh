@@ -34,6 +34,7 @@ struct TcWeight {
 
 struct TcWorkspace {
     int force_bn = 0;                // 0 = pick the tile width from the grid size, else 64 / 128 / 256
+    int use_k256 = 1;                // route K = 256 GEMMs to the resident-A kernel
 };
 
 // Splits W (device fp32 [N][K]) into bf16 planes and encodes the TMA descriptors.

@@ -12,6 +12,8 @@
 
 namespace vapb {
 
+bool g_use_pdl = false;
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__
                                                        const float* __restrict__ cnw,
                                                        const float* __restrict__ cnb,
                                                        float* __restrict__ out, RowMap omap) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_in[kC0PosPerBlock * 5 + 16];
     const int chunk = blockIdx.y;
     const int p0 = blockIdx.x * kC0PosPerBlock;
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__
 void launch_conv0(const float* audio, int n_chunks, int S, int L0, const float* w, const float* b,
                   const float* cnw, const float* cnb, float* out, RowMap omap, cudaStream_t st) {
     dim3 grid((L0 + kC0PosPerBlock - 1) / kC0PosPerBlock, n_chunks);
-    k_conv0_cn_relu<<<grid, 256, 0, st>>>(audio, S, L0, w, b, cnw, cnb, out, omap);
+    launch_k(k_conv0_cn_relu, grid, dim3(256), 0, st, audio, S, L0, w, b, cnw, cnb, out, omap);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -121,6 +125,8 @@ void launch_conv0(const float* audio, int n_chunks, int S, int L0, const float* 
 constexpr int BM = 128, BN = 128, BK = 8, LDS = 132;
 
 __global__ void __launch_bounds__(256) k_sgemm(GemmArgs g) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[2][BK][LDS];
     __shared__ __align__(16) float Bs[2][BK][LDS];
     const int tid = threadIdx.x;
@@ -203,6 +209,8 @@ __global__ void __launch_bounds__(256) k_sgemm(GemmArgs g) {
 constexpr int SM_ = 64, SN_ = 64, SK_ = 32, SLD = 68;
 
 __global__ void __launch_bounds__(256) k_sgemm64(GemmArgs g) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[2][SK_][SLD];
     __shared__ __align__(16) float Bs[2][SK_][SLD];
     const int tid = threadIdx.x;
@@ -279,10 +287,10 @@ void launch_sgemm(const GemmArgs& g, cudaStream_t st) {
     const int big_ctas = ((g.M + BM - 1) / BM) * (g.N / BN);
     if (big_ctas < 100 && g.K % SK_ == 0) {
         dim3 grid((g.M + SM_ - 1) / SM_, g.N / SN_);
-        k_sgemm64<<<grid, 256, 0, st>>>(g);
+        launch_k(k_sgemm64, grid, dim3(256), 0, st, g);
     } else {
         dim3 grid((g.M + BM - 1) / BM, g.N / BN);
-        k_sgemm<<<grid, 256, 0, st>>>(g);
+        launch_k(k_sgemm, grid, dim3(256), 0, st, g);
     }
 }
 
@@ -314,6 +322,8 @@ __device__ __forceinline__ void warp_norm8(float v[8], float denom_inv, const fl
 
 __global__ void __launch_bounds__(256) k_cn_relu(float* X, RowMap map, int M, const float* __restrict__ w,
                                                  const float* __restrict__ b) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -326,12 +336,14 @@ __global__ void __launch_bounds__(256) k_cn_relu(float* X, RowMap map, int M, co
     store_row8(p, lane, v);
 }
 void launch_cn_relu(float* X, RowMap map, int M, const float* w, const float* b, cudaStream_t st) {
-    k_cn_relu<<<(M + 7) / 8, 256, 0, st>>>(X, map, M, w, b);
+    launch_k(k_cn_relu, dim3((M + 7) / 8), dim3(256), 0, st, X, map, M, w, b);
 }
 
 __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ X, RowMap xmap, float* __restrict__ Y,
                                                    RowMap ymap, int M, const float* __restrict__ w,
                                                    const float* __restrict__ b, int gelu) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ X, 
 }
 void launch_layernorm(const float* X, RowMap xmap, float* Y, RowMap ymap, int M, const float* w,
                       const float* b, int gelu, cudaStream_t st) {
-    k_layernorm<<<(M + 7) / 8, 256, 0, st>>>(X, xmap, Y, ymap, M, w, b, gelu);
+    launch_k(k_layernorm, dim3((M + 7) / 8), dim3(256), 0, st, X, xmap, Y, ymap, M, w, b, gelu);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -355,6 +367,8 @@ void launch_layernorm(const float* X, RowMap xmap, float* Y, RowMap ymap, int M,
 // -----------------------------------------------------------------------------------------
 __global__ void k_gather_state(const float* __restrict__ hS, const float* __restrict__ cS,
                                const int* __restrict__ ids, float* hW, float* cW, int B) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;      // float4 index over [2B][64]
     if (i >= B * 2 * 64) return;
     const int n = i / 64, q = i % 64;
@@ -366,10 +380,12 @@ __global__ void k_gather_state(const float* __restrict__ hS, const float* __rest
 void launch_gather_state(const float* hS, const float* cS, const int* ids, float* hW, float* cW, int B,
                          cudaStream_t st) {
     const int n = B * 2 * 64;
-    k_gather_state<<<(n + 255) / 256, 256, 0, st>>>(hS, cS, ids, hW, cW, B);
+    launch_k(k_gather_state, dim3((n + 255) / 256), dim3(256), 0, st, hS, cS, ids, hW, cW, B);
 }
 __global__ void k_scatter_state(float* hS, float* cS, const int* __restrict__ ids, const float* __restrict__ hW,
                                 const float* __restrict__ cW, int B) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * 2 * 64) return;
     const int n = i / 64, q = i % 64;
@@ -381,12 +397,14 @@ __global__ void k_scatter_state(float* hS, float* cS, const int* __restrict__ id
 void launch_scatter_state(float* hS, float* cS, const int* ids, const float* hW, const float* cW, int B,
                           cudaStream_t st) {
     const int n = B * 2 * 64;
-    k_scatter_state<<<(n + 255) / 256, 256, 0, st>>>(hS, cS, ids, hW, cW, B);
+    launch_k(k_scatter_state, dim3((n + 255) / 256), dim3(256), 0, st, hS, cS, ids, hW, cW, B);
 }
 
 // G [n_rows][1024] = W_ih x_t + b_ih + W_hh h + b_hh (already summed by the GEMMs)
 __global__ void k_lstm_cell(const float* __restrict__ G, float* hW, float* cW, float* __restrict__ Y, int n_rows,
                             int n_steps, int step) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows * kD) return;
     const int n = i / kD, d = i % kD;
@@ -401,7 +419,7 @@ __global__ void k_lstm_cell(const float* __restrict__ G, float* hW, float* cW, f
 void launch_lstm_cell(const float* G, float* hW, float* cW, float* Y, int n_rows, int n_steps, int step,
                       cudaStream_t st) {
     const int n = n_rows * kD;
-    k_lstm_cell<<<(n + 255) / 256, 256, 0, st>>>(G, hW, cW, Y, n_rows, n_steps, step);
+    launch_k(k_lstm_cell, dim3((n + 255) / 256), dim3(256), 0, st, G, hW, cW, Y, n_rows, n_steps, step);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -424,6 +442,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
                  float* hS, float* cS, const int* __restrict__ ids,
                  float* __restrict__ Y,             // [NC][n_steps][256]
                  int NC, int n_steps) {
+    pdl_trigger();
     extern __shared__ float lsm[];
     float* sW = lsm;                                   // [256 k][129]  (col = gate*32 + unit)
     float* sH = sW + 256 * kLstmWPitch;                // [2][RT][256]
@@ -441,6 +460,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
 #pragma unroll
         for (int k = lane; k < kD; k += 32) sW[k * kLstmWPitch + col] = __ldg(src + k);
     }
+    pdl_wait();       // the weights above are constants; everything below depends on earlier kernels
     // initial h (all 256 units of the tile's rows) and c (own 32 units)
     for (int i = tid; i < kLstmRT * kD; i += 256) {
         const int r = i >> 8, k = i & 255, n = row0 + r;
@@ -536,7 +556,7 @@ void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* 
         attr_set = true;
     }
     const int tiles = (NC + kLstmRT - 1) / kLstmRT;
-    k_lstm_recurrent<<<tiles * 8, 256, kLstmSmem, st>>>(Gx, Whh, hS, cS, ids, Y, NC, n_steps);
+    launch_k(k_lstm_recurrent, dim3(tiles * 8), dim3(256), kLstmSmem, st, Gx, Whh, hS, cS, ids, Y, NC, n_steps);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -550,6 +570,8 @@ __global__ void __launch_bounds__(256) k_ln_gelu_ring(const float* __restrict__ 
                                                       const float* __restrict__ b, float* ring,
                                                       const int* __restrict__ count, const int* __restrict__ ids,
                                                       int T, float* e_out) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (n >= 2 * B) return;
     const int lane = threadIdx.x & 31;
@@ -565,7 +587,7 @@ __global__ void __launch_bounds__(256) k_ln_gelu_ring(const float* __restrict__ 
 }
 void launch_ln_gelu_ring(const float* X, int B, const float* w, const float* b, float* ring, const int* count,
                          const int* ids, int T, float* e_out, cudaStream_t st) {
-    k_ln_gelu_ring<<<(2 * B + 7) / 8, 256, 0, st>>>(X, B, w, b, ring, count, ids, T, e_out);
+    launch_k(k_ln_gelu_ring, dim3((2 * B + 7) / 8), dim3(256), 0, st, X, B, w, b, ring, count, ids, T, e_out);
 }
 
 // X[(n*T + j)] = ring row of logical position j (oldest first) for j < t, zero rows above.
@@ -573,6 +595,8 @@ void launch_ln_gelu_ring(const float* X, int B, const float* w, const float* b, 
 __global__ void __launch_bounds__(64) k_gather_ring(const float* __restrict__ ring, const int* __restrict__ count,
                                                     const int* __restrict__ ids, float* __restrict__ X,
                                                     int* __restrict__ tvalid, int B, int T) {
+    pdl_trigger();
+    pdl_wait();
     const int j = blockIdx.x, n = blockIdx.y;
     const int b = n >> 1, ch = n & 1;
     const int id = ids[b];
@@ -589,7 +613,7 @@ __global__ void __launch_bounds__(64) k_gather_ring(const float* __restrict__ ri
 void launch_gather_ring(const float* ring, const int* count, const int* ids, float* X, int* tvalid, int B, int T,
                         cudaStream_t st) {
     dim3 grid(T, 2 * B);
-    k_gather_ring<<<grid, 64, 0, st>>>(ring, count, ids, X, tvalid, B, T);
+    launch_k(k_gather_ring, grid, dim3(64), 0, st, ring, count, ids, X, tvalid, B, T);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -600,6 +624,8 @@ void launch_gather_ring(const float* ring, const int* count, const int* ids, flo
 constexpr int kAttnWarps = 8;
 
 __global__ void __launch_bounds__(kAttnWarps * 32) k_attention(AttnArgs a) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float smem[];
     const int T = a.T;
     float* sK = smem;                       // [T][65] (row pitch 65 floats: conflict-free q.k dots)
@@ -685,7 +711,7 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid(a.n_seq, kHeads);
-    k_attention<<<grid, kAttnWarps * 32, smem, st>>>(a);
+    launch_k(k_attention, grid, dim3(kAttnWarps * 32), smem, st, a);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -695,6 +721,8 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 __global__ void __launch_bounds__(256) k_vad(const float* __restrict__ X, const int* __restrict__ tvalid,
                                              const float* __restrict__ w, const float* __restrict__ b,
                                              float* __restrict__ out, int B, int T) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (n >= 2 * B) return;
     const int lane = threadIdx.x & 31;
@@ -710,7 +738,7 @@ __global__ void __launch_bounds__(256) k_vad(const float* __restrict__ X, const 
 }
 void launch_vad(const float* X, const int* tvalid, const float* w, const float* b, float* out, int B, int T,
                 cudaStream_t st) {
-    k_vad<<<(2 * B + 7) / 8, 256, 0, st>>>(X, tvalid, w, b, out, B, T);
+    launch_k(k_vad, dim3((2 * B + 7) / 8), dim3(256), 0, st, X, tvalid, w, b, out, B, T);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -751,6 +779,8 @@ __device__ __forceinline__ void warp_dot256_x4(const float* __restrict__ W, int 
 }
 
 __global__ void __launch_bounds__(kHeadWarps * 32) k_head(HeadArgs a) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sx[2][kD];
     __shared__ float sy[2][kD];
     __shared__ float sh[kD];
@@ -868,6 +898,6 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_head(HeadArgs a) {
     }
     if (tid == 0) a.count[a.ids[b]] += 1;
 }
-void launch_head(const HeadArgs& a, cudaStream_t st) { k_head<<<a.B, kHeadWarps * 32, 0, st>>>(a); }
+void launch_head(const HeadArgs& a, cudaStream_t st) { launch_k(k_head, dim3(a.B), dim3(kHeadWarps * 32), 0, st, a); }
 
 }  // namespace vapb

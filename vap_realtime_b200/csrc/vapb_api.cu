@@ -114,7 +114,7 @@ struct vapb_ctx {
     int last_B = 0;
 
     // options
-    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1;
+    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_pdl = 1;
     std::vector<GraphEntry> graphs;
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -387,6 +387,7 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
 
 void enqueue_step(Step& s) {
     vapb_ctx* c = s.c;
+    vapb::g_use_pdl = c->opt_pdl != 0 && s.prof == nullptr;    // per-kernel event timing needs plain launches
     const int B = s.B, NC = 2 * B, T = c->T;
     cudaStream_t st = s.st;
 
@@ -839,7 +840,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -847,6 +848,8 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         h->graphs.clear();
         if (k == "lstm_fused") h->opt_lstm_fused = value ? 1 : 0;
         else if (k == "fuse_ln") h->opt_fuse_ln = value ? 1 : 0;
+        else if (k == "k256") h->tcws.use_k256 = value ? 1 : 0;
+        else if (k == "pdl") h->opt_pdl = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -873,6 +876,8 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "lstm_fused") *value = h->opt_lstm_fused;
     else if (k == "tile_n") *value = h->opt_tile_n;
     else if (k == "fuse_ln") *value = h->opt_fuse_ln;
+    else if (k == "k256") *value = h->tcws.use_k256;
+    else if (k == "pdl") *value = h->opt_pdl;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
