@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""A/B timing of engine options on the GPU box (whole-step CUDA-graph time, L2 warm)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from vap_realtime_b200.engine import VapEngine
+
+B = int(os.environ.get("B", "64")); T = int(os.environ.get("T", "50"))
+w, _ = bench.load_weights("vap")
+audio = torch.from_numpy(bench.make_audio(B, 8)).cuda()
+configs = {"default": {}, "no_pdl": {"pdl": 0}, "no_k256": {"k256": 0}, "no_k256_no_pdl": {"k256": 0, "pdl": 0},
+           "ln_unfused": {"fuse_ln": 0}, "lstm_unfused": {"lstm_fused": 0}, "gemm_fp32": {"gemm": 0}}
+for name, opts in configs.items():
+    eng = VapEngine(w, 20, T, max_streams=B)
+    eng.set_option("gemm", 1)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    out = torch.empty((B, 6), device="cuda")
+    for i in range(T + 10):
+        eng.step(audio[i % 8], out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(200):
+        eng.step(audio[i % 8], out=out)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name:18s} B={B} T={T}: {e0.elapsed_time(e1) / 200 * 1000:8.1f} us/step  ({eng.last_launch_count} kernels)")
+    eng.close()

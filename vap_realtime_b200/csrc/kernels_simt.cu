@@ -431,11 +431,12 @@ void launch_lstm_cell(const float* G, float* hW, float* cW, float* Y, int n_rows
 // are exchanged through distributed shared memory (st to the 8 peers) + one cluster barrier.
 // Also replaces the gather/scatter of the per-stream (h, c) state.
 // -----------------------------------------------------------------------------------------
-constexpr int kLstmRT = 16;
 constexpr int kLstmWPitch = 129;
 constexpr int kLstmGPitch = 132;
-constexpr size_t kLstmSmem = (size_t)(256 * kLstmWPitch + 2 * kLstmRT * kD + kLstmRT * kLstmGPitch + kLstmRT * 32) * sizeof(float);
+template <int RT>
+constexpr size_t lstm_smem() { return (size_t)(256 * kLstmWPitch + 2 * RT * kD + RT * kLstmGPitch + RT * 32) * sizeof(float); }
 
+template <int kLstmRT>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256)
 k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih z + b_ih + b_hh
                  const float* __restrict__ Whh,     // [1024][256]
@@ -478,30 +479,34 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
-    const int col = tid & 127, rhalf = tid >> 7;       // thread -> one gate column, 8 of the 16 rows
+    constexpr int RH = kLstmRT / 2;                     // rows per thread in the GEMV phase
+    constexpr int RC = kLstmRT / 8;                     // rows per thread in the cell phase
+    const int col = tid & 127, rhalf = tid >> 7;       // thread -> one gate column, half of the rows
     const int gcol = (col >> 5) * kD + 32 * (int)crank + (col & 31);
-    const int cu = tid & 31, cr = tid >> 5;            // cell phase: unit cu, rows cr and cr + 8
+    const int cu = tid & 31, cr = tid >> 5;            // cell phase: unit cu, rows cr + 8 * rr
     uint32_t sH_u32 = (uint32_t)__cvta_generic_to_shared(sH);
-    float h_last[2] = {0.f, 0.f};
+    float h_last[RC];
+#pragma unroll
+    for (int rr = 0; rr < RC; ++rr) h_last[rr] = 0.f;
 
     for (int t = 0; t < n_steps; ++t) {
         const float* hcur = sH + (t & 1) * kLstmRT * kD;
-        float gx[8];
+        float gx[RH];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int n = row0 + rhalf * 8 + r;
+        for (int r = 0; r < RH; ++r) {
+            const int n = row0 + rhalf * RH + r;
             gx[r] = (n < NC) ? __ldg(Gx + ((size_t)n * n_steps + t) * 4 * kD + gcol) : 0.f;
         }
-        float acc[8];
+        float acc[RH];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+        for (int r = 0; r < RH; ++r) acc[r] = 0.f;
 #pragma unroll 2
         for (int k = 0; k < kD; k += 4) {
             const float w0 = sW[(k + 0) * kLstmWPitch + col], w1 = sW[(k + 1) * kLstmWPitch + col];
             const float w2 = sW[(k + 2) * kLstmWPitch + col], w3 = sW[(k + 3) * kLstmWPitch + col];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const float4 hv = *reinterpret_cast<const float4*>(hcur + (rhalf * 8 + r) * kD + k);
+            for (int r = 0; r < RH; ++r) {
+                const float4 hv = *reinterpret_cast<const float4*>(hcur + (rhalf * RH + r) * kD + k);
                 acc[r] = fmaf(w0, hv.x, acc[r]);
                 acc[r] = fmaf(w1, hv.y, acc[r]);
                 acc[r] = fmaf(w2, hv.z, acc[r]);
@@ -509,12 +514,12 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
             }
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) sG[(rhalf * 8 + r) * kLstmGPitch + col] = acc[r] + gx[r];
+        for (int r = 0; r < RH; ++r) sG[(rhalf * RH + r) * kLstmGPitch + col] = acc[r] + gx[r];
         __syncthreads();
         // cell update for (unit cu, rows cr / cr+8); broadcast the new h to all 8 CTAs of the cluster
         const uint32_t nxt_off = (uint32_t)(((t + 1) & 1) * kLstmRT * kD) * 4u;
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
+        for (int rr = 0; rr < RC; ++rr) {
             const int r = cr + 8 * rr;
             const float* gr = sG + r * kLstmGPitch;
             const float gi = gr[cu], gf = gr[32 + cu], gg = gr[64 + cu], go = gr[96 + cu];
@@ -538,7 +543,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
     }
     // persist (h, c) of our 32 units
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
+    for (int rr = 0; rr < RC; ++rr) {
         const int r = cr + 8 * rr, n = row0 + r;
         if (n < NC) {
             const size_t o = ((size_t)ids[n >> 1] * 2 + (n & 1)) * kD + 32 * crank + cu;
@@ -552,11 +557,18 @@ void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* 
                            int n_steps, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_lstm_recurrent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLstmSmem);
+        cudaFuncSetAttribute(k_lstm_recurrent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<8>());
+        cudaFuncSetAttribute(k_lstm_recurrent<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<16>());
         attr_set = true;
     }
-    const int tiles = (NC + kLstmRT - 1) / kLstmRT;
-    launch_k(k_lstm_recurrent, dim3(tiles * 8), dim3(256), kLstmSmem, st, Gx, Whh, hS, cS, ids, Y, NC, n_steps);
+    // 8-row tiles while that still fits one wave of clusters (more SMs busy), 16-row tiles for big batches
+    if ((NC + 7) / 8 * 8 <= 144) {
+        const int tiles = (NC + 7) / 8;
+        launch_k(k_lstm_recurrent<8>, dim3(tiles * 8), dim3(256), lstm_smem<8>(), st, Gx, Whh, hS, cS, ids, Y, NC, n_steps);
+    } else {
+        const int tiles = (NC + 15) / 16;
+        launch_k(k_lstm_recurrent<16>, dim3(tiles * 8), dim3(256), lstm_smem<16>(), st, Gx, Whh, hS, cS, ids, Y, NC, n_steps);
+    }
 }
 
 // -----------------------------------------------------------------------------------------
