@@ -1,0 +1,101 @@
+"""GPU tests of the drop-in surfaces: VAPRealTime (vap + bc), the Vap / VapModel queue API,
+the offline scorer, and the other frame rates (10 Hz, 5 Hz geometry)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, built_asset, chunk
+from oracle.vap_oracle import OracleState, VapOracle, synthetic_audio, chunk_samples
+from vap_realtime_b200 import weights
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vaprealtime_dropin_matches_reference_fixture(fixture_audio):
+    from vap_realtime_b200.vap_main import VAPRealTime
+    audio, ref = fixture_audio
+    vap = VAPRealTime(built_asset("vap_jp_20hz_2500msec.vapw"), None, torch.device("cuda"), 20, 2.5)
+    assert vap.audio_frame_size == 1120 and vap.frame_contxt_padding == 320 and vap.audio_context_len == 50
+    worst = 0.0
+    for n in range(60):
+        c = chunk(audio, n)
+        x1 = c[0].astype(np.float64) if n % 2 else c[0].tolist()          # ndarray and list inputs (vap_main.py:262-267)
+        vap.process_vap(x1, c[1].astype(np.float64))
+        got = list(vap.result_p_now) + list(vap.result_p_future) + [float(vap.result_vad[0][0, 0]), float(vap.result_vad[1][0, 0])]
+        worst = max(worst, np.abs(np.array(got) - ref[n]).max())
+        assert len(vap.current_x1_audio) == 800 and vap.process_time_abs > 0
+        assert tuple(vap.result_vad[0].shape) == (1, 1)
+    assert worst < 1e-4
+    with pytest.raises(RuntimeError):
+        VAPRealTime(built_asset("vap_jp_20hz_2500msec.vapw"), None, torch.device("cpu"), 20, 2.5)
+
+
+def test_bc_dropin(fixture_audio):
+    from vap_realtime_b200.vap_bc_main import VAPRealTime
+    audio, _ = fixture_audio
+    ref = np.load(os.path.join(GOLDEN, "ref_bc_ctx5000.npz"))["out"]
+    vap = VAPRealTime(built_asset("vap_bc_erica_20hz_5000msec.vapw"), None, torch.device("cuda"), 20, 5.0)
+    for n in range(40):
+        c = chunk(audio, n)
+        vap.process_vap(c[0].tolist(), c[1].tolist())
+        assert abs(float(vap.result_p_bc_react[0][0]) - ref[n, 0]) < 1e-4
+        assert abs(float(vap.result_p_bc_emo[0][0]) - ref[n, 1]) < 1e-4
+
+
+def test_vap_queue_api(fixture_audio):
+    from vap_realtime_b200 import Vap, VapInput, VapModel
+    assert VapModel is Vap
+    audio, _ = fixture_audio
+    n = 30
+    a = audio[:, : 800 * n].astype(np.float64)
+    vap = Vap(mode="vap", frame_rate=20, context_len_sec=2.5, mic1=VapInput.Array(a[0]), mic2=VapInput.Array(a[1]), device="cuda")
+    vap.start_process()
+    oracle = VapOracle(weights.load(built_asset("vap_jp_20hz_2500msec.vapw")), 20, 50, "vap")
+    st = OracleState(1)
+    x = np.concatenate([np.zeros((2, 320)), a], axis=1).astype(np.float32)       # the worker starts with 320 zeros
+    for k in range(n - 1):
+        r = vap.get_result()
+        want = oracle.step(x[None, :, 800 * k: 800 * k + 1120], st).numpy()[0]
+        assert set(r) == {"t", "x1", "x2", "p_now", "p_future", "vad"}
+        assert np.abs(np.array(r["p_now"] + r["p_future"] + r["vad"]) - want).max() < 1e-4
+        assert len(r["x1"]) == 800
+
+
+def test_offline_scorer_head(tmp_path):
+    from vap_realtime_b200 import vap_offline
+    from vap_realtime_b200.vap_main import VAPRealTime
+    d = np.load(os.path.join(GOLDEN, "ref_offline_head.npz"))
+    audio = d["audio"].astype(np.float32) / 32768.0
+    vap = VAPRealTime(built_asset("vap_jp_20hz_2500msec.vapw"), None, torch.device("cuda"), 20, 2.5)
+    res = vap_offline.run(vap, audio[0], audio[1])
+    out = tmp_path / "o.txt"
+    vap_offline.write_csv(str(out), res)
+    got = np.loadtxt(out, delimiter=",", skiprows=1)
+    rows = d["golden_rows"]
+    assert got.shape == rows.shape
+    assert np.allclose(got[:, 0], rows[:, 0]) and np.abs(got[:, 1:] - rows[:, 1:]).max() < 1e-4
+    assert open(out).readline().startswith("time_sec,p_now(0=left)")
+
+
+@pytest.mark.parametrize("hz", [10, 5])
+def test_other_frame_rates_random_weights(hz):
+    """10 Hz (chunk 1 920 -> 12 conv frames -> 10 LSTM steps, downsample k=10) and 5 Hz (3 520 -> 22 -> 20, k=20)."""
+    from vap_realtime_b200.engine import VapEngine
+    w = weights.random_tensors(seed=21, frame_hz=hz)
+    T, B, n_steps = 8, 3, 14
+    oracle = VapOracle(w, hz, T, "vap")
+    eng = VapEngine(w, hz, T, max_streams=B)
+    eng.set_option("gemm", 1)
+    assert eng.chunk_samples == chunk_samples(hz)
+    audio = np.stack([synthetic_audio(s, n_steps, hz) for s in range(B)])
+    st = OracleState(B)
+    worst = 0.0
+    for n in range(n_steps):
+        a = np.ascontiguousarray(chunk(audio, n, hz))
+        got = eng.step(torch.from_numpy(a).cuda()).cpu().numpy()
+        want = oracle.step(a, st).numpy()
+        worst = max(worst, np.abs(got - want).max())
+    print(f"{hz} Hz: max|d| = {worst:.2e}")
+    assert worst < 1e-4
