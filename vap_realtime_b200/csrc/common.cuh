@@ -114,6 +114,9 @@ struct AttnArgs {
     int sibling;                   // 1: K/V rows come from the other channel of the same stream
 };
 void launch_attention(const AttnArgs& a, cudaStream_t st);
+// last-row-only variants used when the final cross layer is pruned to the newest frame
+void launch_gather_last(const float* X, const int* tvalid, float* Xl, int n_seq, int T, cudaStream_t st);
+void launch_attention_last(const AttnArgs& a, cudaStream_t st);   // Q, O: [n_seq][256] compact; K, V: full rows
 void launch_vad(const float* X, const int* tvalid, const float* w, const float* b, float* out, int B, int T,
                 cudaStream_t st);
 struct HeadArgs {
@@ -126,6 +129,7 @@ struct HeadArgs {
     float* logits_tap;         // [B][256] or nullptr
     int* count; const int* ids;
     int B, T, head_kind;
+    int compact;               // 1: X is [2B][256] (one row per sequence: the newest frame)
 };
 void launch_head(const HeadArgs& a, cudaStream_t st);
 

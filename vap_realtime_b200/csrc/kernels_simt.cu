@@ -454,12 +454,26 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = (blockIdx.x >> 3) * kLstmRT;
 
-    // W_hh slice -> smem: for each of the 128 local columns, 256 contiguous k (coalesced read)
-    for (int col = warp; col < 128; col += 8) {
-        const int grow = (col >> 5) * kD + 32 * (int)crank + (col & 31);
-        const float* src = Whh + (size_t)grow * kD;
+    // W_hh slice -> smem, transposed to [k][col]: 128 columns x 64 float4 along k, 8 loads in flight per thread
+#pragma unroll 1
+    for (int base = 0; base < 128 * 64; base += 256 * 8) {
+        float4 v[8];
 #pragma unroll
-        for (int k = lane; k < kD; k += 32) sW[k * kLstmWPitch + col] = __ldg(src + k);
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * 256 + tid;              // (col, k-quad); consecutive lanes -> consecutive k
+            const int col = idx >> 6, kq = idx & 63;
+            const int grow = (col >> 5) * kD + 32 * (int)crank + (col & 31);
+            v[u] = __ldg(reinterpret_cast<const float4*>(Whh + (size_t)grow * kD) + kq);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * 256 + tid;
+            const int col = idx >> 6, k = (idx & 63) * 4;
+            sW[(k + 0) * kLstmWPitch + col] = v[u].x;
+            sW[(k + 1) * kLstmWPitch + col] = v[u].y;
+            sW[(k + 2) * kLstmWPitch + col] = v[u].z;
+            sW[(k + 3) * kLstmWPitch + col] = v[u].w;
+        }
     }
     pdl_wait();       // the weights above are constants; everything below depends on earlier kernels
     // initial h (all 256 units of the tile's rows) and c (own 32 units)
@@ -727,6 +741,92 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
 }
 
 // -----------------------------------------------------------------------------------------
+// Last-frame pruning of the final cross layer: only position t-1 of every sequence feeds the
+// head (vap_main.py:316-317 takes [-1]), so its query-side work runs on one row per sequence.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_last(const float* __restrict__ X, const int* __restrict__ tvalid,
+                                                     float* __restrict__ Xl, int n_seq, int T) {
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= n_seq) return;
+    const int lane = threadIdx.x & 31;
+    const int t = tvalid[n >> 1];
+    float v[8];
+    load_row8(X + ((size_t)n * T + (t - 1)) * kD, lane, v);
+    store_row8(Xl + (size_t)n * kD, lane, v);
+}
+void launch_gather_last(const float* X, const int* tvalid, float* Xl, int n_seq, int T, cudaStream_t st) {
+    launch_k(k_gather_last, dim3((n_seq + 7) / 8), dim3(256), 0, st, X, tvalid, Xl, n_seq, T);
+}
+
+// one warp per (sequence, head); the query is the newest frame, so every valid key j < t is visible
+__global__ void __launch_bounds__(128) k_attention_last(AttnArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = a.T;
+    const int t = a.tvalid[n >> 1];
+    const int kvn = a.sibling ? (n ^ 1) : n;
+    float q[64];
+    const float4* qp = reinterpret_cast<const float4*>(a.Q + (size_t)n * a.ldq + h * 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float4 v = __ldg(qp + i);
+        q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+    }
+    const float slope = a.slopes[h];
+    float s[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int j = lane + 32 * jj;
+        s[jj] = -INFINITY;
+        if (j < t) {
+            const float4* kp = reinterpret_cast<const float4*>(a.K + ((size_t)kvn * T + j) * a.ldk + h * 64);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 v = kp[i];
+                acc = fmaf(q[4 * i], v.x, acc);
+                acc = fmaf(q[4 * i + 1], v.y, acc);
+                acc = fmaf(q[4 * i + 2], v.z, acc);
+                acc = fmaf(q[4 * i + 3], v.w, acc);
+            }
+            s[jj] = acc * 0.0625f + slope * (float)j;
+        }
+        mx = fmaxf(mx, s[jj]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int j = lane + 32 * jj;
+        s[jj] = (j < t) ? expf(s[jj] - mx) : 0.f;
+        sum += s[jj];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int jend = min(32, t - 32 * jj);
+        for (int l = 0; l < jend; ++l) {
+            const float pj = __shfl_sync(0xffffffffu, s[jj], l) * inv;
+            const float* vr = a.V + ((size_t)kvn * T + (32 * jj + l)) * a.ldv + h * 64;
+            o0 = fmaf(pj, vr[lane], o0);
+            o1 = fmaf(pj, vr[lane + 32], o1);
+        }
+    }
+    float* orow = a.O + (size_t)n * a.ldo + h * 64;
+    orow[lane] = o0;
+    orow[lane + 32] = o1;
+}
+void launch_attention_last(const AttnArgs& a, cudaStream_t st) {
+    launch_k(k_attention_last, dim3(a.n_seq), dim3(128), 0, st, a);
+}
+
+// -----------------------------------------------------------------------------------------
 // vad = sigmoid(va_classifier(ar_channel output at the last valid frame))
 // (vap_main.py:292-293, 313-314).  One warp per (stream, channel).
 // -----------------------------------------------------------------------------------------
@@ -802,8 +902,10 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_head(HeadArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = a.tvalid[b];
     if (tid < kD) {
-        sx[0][tid] = a.X[((size_t)(2 * b) * a.T + (t - 1)) * kD + tid];
-        sx[1][tid] = a.X[((size_t)(2 * b + 1) * a.T + (t - 1)) * kD + tid];
+        const size_t r0 = a.compact ? (size_t)(2 * b) : ((size_t)(2 * b) * a.T + (t - 1));
+        const size_t r1 = a.compact ? (size_t)(2 * b + 1) : ((size_t)(2 * b + 1) * a.T + (t - 1));
+        sx[0][tid] = a.X[r0 * kD + tid];
+        sx[1][tid] = a.X[r1 * kD + tid];
     }
     __syncthreads();
     for (int o0 = warp * 4; o0 < kD; o0 += kHeadWarps * 4) {

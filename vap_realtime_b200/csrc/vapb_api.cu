@@ -42,6 +42,7 @@ struct AttnWeights {
     float* Wproj;            // [256][256]
     float* slopes;           // [4]
     TcWeight tc_qkv, tc_proj;
+    TcWeight tc_q, tc_kv;    // rows [0,256) and [256,768) of Wqkv, used when the layer is pruned to the last frame
 };
 struct LayerWeights {
     float *ln_sa_w, *ln_sa_b, *ln_ff_w, *ln_ff_b;
@@ -103,6 +104,7 @@ struct vapb_ctx {
     int halo[5] = {0, 0, 0, 0, 0};
     float *hW = nullptr, *cW = nullptr, *Gx = nullptr, *Gt = nullptr, *Y = nullptr, *dsout = nullptr, *ebuf = nullptr;
     float *X = nullptr, *Z = nullptr, *QKV = nullptr, *O = nullptr, *Hd = nullptr, *KVc = nullptr, *Qc = nullptr;
+    float *Xl = nullptr, *Zl = nullptr, *Ql = nullptr, *Ol = nullptr, *Hl = nullptr;   // one row per sequence (pruned layer)
     float* audio_stage = nullptr;    // device staging for vapb_step_host
     float* out_stage = nullptr;
     TcWorkspace tcws;                // bf16 hi/lo activation planes for the tcgen05 path
@@ -114,7 +116,7 @@ struct vapb_ctx {
     int last_B = 0;
 
     // options
-    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_pdl = 0;   // PDL measured slower inside CUDA graphs on this driver (ablation in profiles/)
+    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_prune = 1, opt_pdl = 0;   // PDL measured slower inside CUDA graphs on this driver (ablation in profiles/)
     std::vector<GraphEntry> graphs;
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -385,6 +387,46 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
     gemm(s, "gemm_ffn2", c->Hd, pf, lw.W2, &lw.tc_w2, nullptr, c->X, pd, c->X, pd, R, kD, kFF, 0);
 }
 
+// Final cross layer with the query side restricted to the newest frame of every sequence (exact:
+// nothing downstream reads the other positions, vap_main.py:316-317).  K/V still cover the window.
+void transformer_layer_last(Step& s, const LayerWeights& lw) {
+    vapb_ctx* c = s.c;
+    const int NL = 2 * s.B, R = NL * c->T;
+    const RowMap pd = plain_map(kD), pf = plain_map(kFF), p2 = plain_map(2 * kD);
+    const bool fuse_ln = c->opt_gemm == 1 && c->opt_fuse_ln;
+    auto ln_gemm = [&](const char* tag, const float* A, float* Z, int M, const float* lnw, const float* lnb, const float* W,
+                       const TcWeight* tcw, float* C, RowMap cm, int N, int act) {
+        if (fuse_ln) {
+            gemm(s, tag, A, pd, W, tcw, nullptr, nullptr, pd, C, cm, M, N, kD, act, lnw, lnb);
+        } else {
+            launch_layernorm(A, pd, Z, pd, M, lnw, lnb, 0, s.st); mark(s, "layernorm");
+            gemm(s, tag, Z, pd, W, tcw, nullptr, nullptr, pd, C, cm, M, N, kD, act);
+        }
+    };
+    auto attn_last = [&](const float* Q, const float* K, const float* V, int ldkv, const float* slopes, int sibling) {
+        AttnArgs a;
+        a.Q = Q; a.ldq = kD; a.K = K; a.ldk = ldkv; a.V = V; a.ldv = ldkv; a.O = c->Ol; a.ldo = kD;
+        a.tvalid = c->tvalid; a.slopes = slopes; a.n_seq = NL; a.T = c->T; a.sibling = sibling;
+        launch_attention_last(a, s.st);
+        mark(s, sibling ? "attn_cross_last" : "attn_self_last");
+    };
+    // keys / values over the whole window: cross attention from the RAW sibling input, self attention from LN(X)
+    gemm(s, "gemm_kv_cross", c->X, pd, lw.Wkv_c, &lw.tc_kv_c, nullptr, nullptr, pd, c->KVc, p2, R, 2 * kD, kD, 0);
+    ln_gemm("gemm_ln_kv_self", c->X, c->Z, R, lw.ln_sa_w, lw.ln_sa_b, lw.sa.Wqkv + (size_t)kD * kD, &lw.sa.tc_kv, c->QKV, p2, 2 * kD, 0);
+    launch_gather_last(c->X, c->tvalid, c->Xl, NL, c->T, s.st); mark(s, "gather_last");
+    // self attention of the newest frame
+    ln_gemm("gemm_ln_q_last", c->Xl, c->Zl, NL, lw.ln_sa_w, lw.ln_sa_b, lw.sa.Wqkv, &lw.sa.tc_q, c->Ql, pd, kD, 0);
+    attn_last(c->Ql, c->QKV, c->QKV + kD, 2 * kD, lw.sa.slopes, 0);
+    gemm(s, "gemm_proj_last", c->Ol, pd, lw.sa.Wproj, &lw.sa.tc_proj, nullptr, c->Xl, pd, c->Xl, pd, NL, kD, kD, 0);
+    // cross attention
+    ln_gemm("gemm_ln_q_cross_last", c->Xl, c->Zl, NL, lw.ln_src_w, lw.ln_src_b, lw.Wq_c, &lw.tc_q_c, c->Ql, pd, kD, 0);
+    attn_last(c->Ql, c->KVc, c->KVc + kD, 2 * kD, lw.slopes_c, 1);
+    gemm(s, "gemm_proj_last", c->Ol, pd, lw.Wproj_c, &lw.tc_proj_c, nullptr, c->Xl, pd, c->Xl, pd, NL, kD, kD, 0);
+    // feed forward
+    ln_gemm("gemm_ln_ffn1_last", c->Xl, c->Zl, NL, lw.ln_ff_w, lw.ln_ff_b, lw.W1, &lw.tc_w1, c->Hl, pf, kFF, 1);
+    gemm(s, "gemm_ffn2_last", c->Hl, pf, lw.W2, &lw.tc_w2, nullptr, c->Xl, pd, c->Xl, pd, NL, kD, kFF, 0);
+}
+
 void enqueue_step(Step& s) {
     vapb_ctx* c = s.c;
     vapb::g_use_pdl = c->opt_pdl != 0 && s.prof == nullptr;    // per-kernel event timing needs plain launches
@@ -449,13 +491,15 @@ void enqueue_step(Step& s) {
         launch_vad(c->X, c->tvalid, c->va_w, c->va_b, s.out, B, T, st); mark(s, "vad");
     }
     // ---- ar: three TransformerStereoLayers (modules.py:289-300, 395-423)
+    const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
     for (int li = 0; li < 3; ++li) {
-        transformer_layer(s, c->layers[1 + li]);
+        if (li == 2 && prune) transformer_layer_last(s, c->layers[3]);
+        else transformer_layer(s, c->layers[1 + li]);
         tap_copy(s, c->tap_cross[li], c->X, RX);
     }
     // ---- combinator + projection head + aggregation; advances the frame counters
     HeadArgs h;
-    h.X = c->X; h.tvalid = c->tvalid; h.Wa = c->Wa; h.Wb = c->Wb; h.lnw = c->comb_lnw; h.lnb = c->comb_lnb;
+    h.X = prune ? c->Xl : c->X; h.compact = prune ? 1 : 0; h.tvalid = c->tvalid; h.Wa = c->Wa; h.Wb = c->Wb; h.lnw = c->comb_lnw; h.lnb = c->comb_lnb;
     h.Wh = c->Wh; h.bh = c->bh; h.n_out = c->n_out; h.out = s.out;
     h.comb_tap = c->opt_keep_taps ? c->tap_comb : nullptr;
     h.logits_tap = c->opt_keep_taps ? c->tap_logits : nullptr;
@@ -613,6 +657,11 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     DA(c->Hd, R * kFF);
     DA(c->KVc, R * 2 * kD);
     DA(c->Qc, R * kD);
+    DA(c->Xl, NC * kD);
+    DA(c->Zl, NC * kD);
+    DA(c->Ql, NC * kD);
+    DA(c->Ol, NC * kD);
+    DA(c->Hl, NC * kFF);
     DA(c->audio_stage, MB * 2 * c->S);
     DA(c->out_stage, MB * 6);
 #undef DA
@@ -639,6 +688,8 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         for (int l = 0; l < 4 && ok; ++l) {
             LayerWeights& lw = c->layers[l];
             ok = tc_prepare_weight(lw.sa.Wqkv, 3 * kD, kD, lw.sa.tc_qkv, c->allocs, terr) &&
+                 tc_prepare_weight(lw.sa.Wqkv, kD, kD, lw.sa.tc_q, c->allocs, terr) &&
+                 tc_prepare_weight(lw.sa.Wqkv + (size_t)kD * kD, 2 * kD, kD, lw.sa.tc_kv, c->allocs, terr) &&
                  tc_prepare_weight(lw.sa.Wproj, kD, kD, lw.sa.tc_proj, c->allocs, terr) &&
                  tc_prepare_weight(lw.W1, kFF, kD, lw.tc_w1, c->allocs, terr) &&
                  tc_prepare_weight(lw.W2, kD, kFF, lw.tc_w2, c->allocs, terr);
@@ -840,7 +891,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -850,6 +901,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "fuse_ln") h->opt_fuse_ln = value ? 1 : 0;
         else if (k == "k256") h->tcws.use_k256 = value ? 1 : 0;
         else if (k == "pdl") h->opt_pdl = value ? 1 : 0;
+        else if (k == "prune") h->opt_prune = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -878,6 +930,7 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "fuse_ln") *value = h->opt_fuse_ln;
     else if (k == "k256") *value = h->tcws.use_k256;
     else if (k == "pdl") *value = h->opt_pdl;
+    else if (k == "prune") *value = h->opt_prune;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
