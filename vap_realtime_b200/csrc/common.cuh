@@ -66,6 +66,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 extern bool g_use_pdl;      // set by the step driver before it enqueues kernels
+extern bool g_attn_rk;
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

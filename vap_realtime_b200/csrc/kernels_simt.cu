@@ -13,6 +13,7 @@
 namespace vapb {
 
 bool g_use_pdl = false;
+bool g_attn_rk = true;      // register-resident-K attention for T <= 64 (option "attn_rk")
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -729,7 +730,141 @@ __global__ void __launch_bounds__(kAttnWarps * 32) k_attention(AttnArgs a) {
         __syncwarp();
     }
 }
+// -----------------------------------------------------------------------------------------
+// Attention for windows of at most 64 frames (the 2.5 s / 3 s models): the K rows of the
+// (sequence, head) live in REGISTERS (lane j holds keys j and j+32), four query rows are processed
+// per pass so that each broadcast q / p / V read from shared memory feeds 8..32 FMAs.
+// Same arithmetic as k_attention (fp32 FMA, exact softmax).
+// -----------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(128) k_attention_rk(AttnArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float smem[];
+    const int T = a.T;
+    float* sV = smem;                          // [T][64]
+    float* sQ = sV + T * 64;                   // [4 warps][4 rows][64]
+    float* sP = sQ + 4 * 4 * 64;               // [4 warps][64 keys][4 rows]
+    const int n = blockIdx.x, h = blockIdx.y;
+    const int t = a.tvalid[n >> 1];
+    const int kvn = a.sibling ? (n ^ 1) : n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < t * 16; i += blockDim.x) {
+        const int j = i >> 4, q = (i & 15) * 4;
+        *reinterpret_cast<float4*>(sV + j * 64 + q) =
+            *reinterpret_cast<const float4*>(a.V + ((size_t)kvn * T + j) * a.ldv + h * 64 + q);
+    }
+    float kreg[KC][64];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        const int j = lane + 32 * c;
+        if (j < t) {
+            const float4* kp = reinterpret_cast<const float4*>(a.K + ((size_t)kvn * T + j) * a.ldk + h * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 v = kp[i];
+                kreg[c][4 * i] = v.x; kreg[c][4 * i + 1] = v.y; kreg[c][4 * i + 2] = v.z; kreg[c][4 * i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) kreg[c][i] = 0.f;
+        }
+    }
+    __syncthreads();
+    const float slope = a.slopes[h];
+    float* q = sQ + warp * 256;
+    float* p = sP + warp * 256;
+    for (int i0 = warp * 4; i0 < T; i0 += 16) {
+        {   // four query rows -> smem (256 B per row, coalesced)
+            const int r = lane >> 3, c8 = (lane & 7) * 8;
+            const int i = min(i0 + r, T - 1);
+            const float4* qp = reinterpret_cast<const float4*>(a.Q + ((size_t)n * T + i) * a.ldq + h * 64 + c8);
+            *reinterpret_cast<float4*>(q + r * 64 + c8) = qp[0];
+            *reinterpret_cast<float4*>(q + r * 64 + c8 + 4) = qp[1];
+        }
+        __syncwarp();
+        float acc[KC][4];
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[c][r] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 64; d += 4) {
+            float4 q4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) q4[r] = *reinterpret_cast<const float4*>(q + r * 64 + d);
+#pragma unroll
+            for (int c = 0; c < KC; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    acc[c][r] = fmaf(q4[r].x, kreg[c][d], acc[c][r]);
+                    acc[c][r] = fmaf(q4[r].y, kreg[c][d + 1], acc[c][r]);
+                    acc[c][r] = fmaf(q4[r].z, kreg[c][d + 2], acc[c][r]);
+                    acc[c][r] = fmaf(q4[r].w, kreg[c][d + 3], acc[c][r]);
+                }
+        }
+        float pr[KC][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = i0 + r;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                const int j = lane + 32 * c;
+                const float sc = (j <= i && j < t) ? (acc[c][r] * 0.0625f + slope * (float)j) : -INFINITY;
+                pr[c][r] = sc;
+                mx = fmaxf(mx, sc);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                const float e = (pr[c][r] == -INFINITY) ? 0.f : expf(pr[c][r] - mx);
+                pr[c][r] = e;
+                sum += e;
+            }
+            sum = warp_sum(sum);
+            const float inv = (i < t) ? (1.0f / sum) : 0.f;      // rows beyond the window produce zeros
+#pragma unroll
+            for (int c = 0; c < KC; ++c) pr[c][r] = (i < t) ? pr[c][r] * inv : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+            *reinterpret_cast<float4*>(p + (lane + 32 * c) * 4) = make_float4(pr[c][0], pr[c][1], pr[c][2], pr[c][3]);
+        __syncwarp();
+        float o[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[r][0] = o[r][1] = 0.f;
+        const int jmax = min(min(i0 + 3, T - 1), t - 1);
+        for (int j = 0; j <= jmax; ++j) {
+            const float4 p4 = *reinterpret_cast<const float4*>(p + j * 4);
+            const float v0 = sV[j * 64 + lane], v1 = sV[j * 64 + lane + 32];
+            o[0][0] = fmaf(p4.x, v0, o[0][0]); o[0][1] = fmaf(p4.x, v1, o[0][1]);
+            o[1][0] = fmaf(p4.y, v0, o[1][0]); o[1][1] = fmaf(p4.y, v1, o[1][1]);
+            o[2][0] = fmaf(p4.z, v0, o[2][0]); o[2][1] = fmaf(p4.z, v1, o[2][1]);
+            o[3][0] = fmaf(p4.w, v0, o[3][0]); o[3][1] = fmaf(p4.w, v1, o[3][1]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = i0 + r;
+            if (i < T) {
+                float* orow = a.O + ((size_t)n * T + i) * a.ldo + h * 64;
+                orow[lane] = o[r][0];
+                orow[lane + 32] = o[r][1];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 void launch_attention(const AttnArgs& a, cudaStream_t st) {
+    if (a.T <= 64 && g_attn_rk) {
+        const size_t sm = (size_t)(a.T * 64 + 4 * 256 + 4 * 256) * sizeof(float);
+        dim3 grid(a.n_seq, kHeads);
+        if (a.T <= 32) launch_k(k_attention_rk<1>, grid, dim3(128), sm, st, a);
+        else launch_k(k_attention_rk<2>, grid, dim3(128), sm, st, a);
+        return;
+    }
     const size_t smem = (size_t)(((a.T * 65 + 3) & ~3) + a.T * 64 + kAttnWarps * 64 + kAttnWarps * 128) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {

@@ -116,7 +116,7 @@ struct vapb_ctx {
     int last_B = 0;
 
     // options
-    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_prune = 1, opt_pdl = 0;   // PDL measured slower inside CUDA graphs on this driver (ablation in profiles/)
+    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_prune = 1, opt_attn_rk = 1, opt_fork = 1, opt_pdl = 0;   // PDL measured slower inside CUDA graphs on this driver (ablation in profiles/)
     std::vector<GraphEntry> graphs;
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -125,6 +125,10 @@ struct vapb_ctx {
     // bridged onto this internal stream with events (stream order is preserved for the caller).
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    // side branch of the step graph: the cross-attention K/V projection only needs the layer input,
+    // so it runs next to the LN -> QKV -> attention -> proj chain instead of in front of it
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -351,10 +355,22 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
     vapb_ctx* c = s.c;
     const int R = 2 * s.B * c->T;
     const RowMap pd = plain_map(kD), pf = plain_map(kFF), p3 = plain_map(3 * kD), p2 = plain_map(2 * kD);
+    // K/V of the cross attention come from the RAW layer input of the sibling channel
+    // (modules.py:276-283): projected from X before the proj GEMM updates X in place.  With "fork" the
+    // projection runs on a side branch, concurrently with LN -> QKV -> attention.
+    const bool fork = lw.cross && c->opt_fork && s.prof == nullptr;
     if (lw.cross) {
-        // K/V of the cross attention come from the RAW layer input of the sibling channel
-        // (modules.py:276-283), so project it before X is updated in place.
+        cudaStream_t main_st = s.st;
+        if (fork) {
+            cudaEventRecord(c->ev_fork, main_st);
+            cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0);
+            s.st = c->side_stream;
+        }
         gemm(s, "gemm_kv_cross", c->X, pd, lw.Wkv_c, &lw.tc_kv_c, nullptr, nullptr, pd, c->KVc, p2, R, 2 * kD, kD, 0);
+        if (fork) {
+            cudaEventRecord(c->ev_join, c->side_stream);
+            s.st = main_st;
+        }
     }
     // self attention block (modules.py:268-272)
     // LayerNorm is a prologue of the consuming GEMM on the tensor-core path, a kernel of its own otherwise
@@ -366,6 +382,7 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
         gemm(s, "gemm_qkv", c->Z, pd, lw.sa.Wqkv, &lw.sa.tc_qkv, nullptr, nullptr, pd, c->QKV, p3, R, 3 * kD, kD, 0);
     }
     attention(s, c->QKV, 3 * kD, c->QKV + kD, 3 * kD, c->QKV + 2 * kD, 3 * kD, c->O, lw.sa.slopes, 0);
+    if (fork) cudaStreamWaitEvent(s.st, c->ev_join, 0);      // X is overwritten next: the side branch must have read it
     gemm(s, "gemm_proj", c->O, pd, lw.sa.Wproj, &lw.sa.tc_proj, nullptr, c->X, pd, c->X, pd, R, kD, kD, 0);
     if (lw.cross) {
         if (fuse_ln) {
@@ -430,6 +447,7 @@ void transformer_layer_last(Step& s, const LayerWeights& lw) {
 void enqueue_step(Step& s) {
     vapb_ctx* c = s.c;
     vapb::g_use_pdl = c->opt_pdl != 0 && s.prof == nullptr;    // per-kernel event timing needs plain launches
+    vapb::g_attn_rk = c->opt_attn_rk != 0;
     const int B = s.B, NC = 2 * B, T = c->T;
     cudaStream_t st = s.st;
 
@@ -676,8 +694,11 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     cudaEventCreate(&c->ev1);
     cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess)
         FAIL_CREATE(VAPB_ECUDA, "cudaStreamCreate failed");
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
 
     // ---- tcgen05 operands: bf16 hi/lo planes of every tensor-core GEMM weight (+ workspaces)
     {
@@ -723,6 +744,9 @@ int vapb_destroy(vapb_handle h) {
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return VAPB_OK;
 }
@@ -891,7 +915,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -902,6 +926,8 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "k256") h->tcws.use_k256 = value ? 1 : 0;
         else if (k == "pdl") h->opt_pdl = value ? 1 : 0;
         else if (k == "prune") h->opt_prune = value ? 1 : 0;
+        else if (k == "attn_rk") h->opt_attn_rk = value ? 1 : 0;
+        else if (k == "fork") h->opt_fork = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -931,6 +957,8 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "k256") *value = h->tcws.use_k256;
     else if (k == "pdl") *value = h->opt_pdl;
     else if (k == "prune") *value = h->opt_prune;
+    else if (k == "attn_rk") *value = h->opt_attn_rk;
+    else if (k == "fork") *value = h->opt_fork;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
