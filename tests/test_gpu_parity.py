@@ -35,7 +35,7 @@ def replay(engine, audio, n, ids=None):
 
 
 # case + 16 * tile selector (0 = automatic, 1/2/3 = force N tile 64/128/256)
-SELFTEST_VARIANTS = list(range(8)) + [16 + 6, 32 + 7, 48 + 6] + [16 + 0, 16 + 2, 16 + 5, 32 + 1, 32 + 4, 32 + 5, 48 + 0, 48 + 2, 48 + 3]
+SELFTEST_VARIANTS = list(range(8)) + [14] + [16 + 6, 32 + 7, 48 + 6] + [16 + 0, 16 + 2, 16 + 5, 32 + 1, 32 + 4, 32 + 5, 48 + 0, 48 + 2, 48 + 3]
 
 
 @pytest.mark.parametrize("variant", SELFTEST_VARIANTS)
@@ -176,7 +176,7 @@ def test_option_variants_agree(vap_weights, fixture_audio):
     audio, ref = fixture_audio
     outs = {}
     for name, opts in {"default": {}, "lstm_unfused": {"lstm_fused": 0}, "tile64": {"tile_n": 64},
-                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}, "ln_unfused": {"fuse_ln": 0}, "no_k256": {"k256": 0}, "pdl": {"pdl": 1}, "no_prune": {"prune": 0}, "attn_smem": {"attn_rk": 0}, "no_fork": {"fork": 0}}.items():
+                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}, "ln_unfused": {"fuse_ln": 0}, "no_k256": {"k256": 0}, "pdl": {"pdl": 1}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}}.items():
         eng = VapEngine(vap_weights, 20, 50, max_streams=3)
         eng.set_option("gemm", DEF)
         for k, v in opts.items():

@@ -54,7 +54,11 @@ struct GemmArgs {
     // K == 256 only): A_norm = (A - mean) * rsqrt(var + 1e-5) * ln_w + ln_b  (biased variance).
     const float* ln_w = nullptr;
     const float* ln_b = nullptr;
-    long long* dbg = nullptr;     // optional: 8 clock64 stamps per CTA (self-test / tuning only)
+    long long* dbg = nullptr;     // optional: clock64 stamps per CTA (self-test / tuning only)
+    // split-K (tcgen05 generic kernel): grid.z = ksplit CTAs each take K/ksplit; partial z is written to
+    // C + z * csplit_stride (no activation / residual; bias only in partial 0); the consumer sums them.
+    int ksplit = 1;
+    long long csplit_stride = 0;
 };
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------
@@ -88,7 +92,8 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 void launch_conv0(const float* audio, int n_chunks, int S, int L0, const float* w, const float* b,
                   const float* cnw, const float* cnb, float* out, RowMap omap, cudaStream_t st);
 void launch_sgemm(const GemmArgs& g, cudaStream_t st);
-void launch_cn_relu(float* X, RowMap map, int M, const float* w, const float* b, cudaStream_t st);
+void launch_cn_relu(float* X, RowMap map, int M, const float* w, const float* b, cudaStream_t st,
+                    const float* partials = nullptr, int nsplit = 0, long long split_stride = 0);
 void launch_layernorm(const float* X, RowMap xmap, float* Y, RowMap ymap, int M, const float* w,
                       const float* b, int gelu, cudaStream_t st);
 void launch_gather_state(const float* hS, const float* cS, const int* ids, float* hW, float* cW, int B,
@@ -100,7 +105,8 @@ void launch_lstm_cell(const float* G, float* hW, float* cW, float* Y, int n_rows
 void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* cS, const int* ids, float* Y, int NC,
                            int n_steps, cudaStream_t st);
 void launch_ln_gelu_ring(const float* X, int B, const float* w, const float* b, float* ring,
-                         const int* count, const int* ids, int T, float* e_out, cudaStream_t st);
+                         const int* count, const int* ids, int T, float* e_out, cudaStream_t st,
+                         int nsplit = 1, long long split_stride = 0);
 void launch_gather_ring(const float* ring, const int* count, const int* ids, float* X, int* tvalid, int B,
                         int T, cudaStream_t st);
 struct AttnArgs {

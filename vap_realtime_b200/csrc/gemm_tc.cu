@@ -248,7 +248,8 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
-    const int nkb = g.K / kBK;
+    const int nkb = g.K / kBK / g.ksplit;            // k-blocks of this CTA (split-K along grid.z)
+    const int kb_off = blockIdx.z * nkb;
 
     if (warp == kProducerWarps && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) {
@@ -266,7 +267,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    long long* dbg = g.dbg ? g.dbg + 8 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    long long* dbg = g.dbg ? g.dbg + 16 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
     if (dbg && tid == 0) dbg[0] = clock64();
 
     if (warp < kProducerWarps) {
@@ -279,7 +280,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int m = m0 + r0 + 32 * i;
-            rowp[i] = (m < g.M) ? (g.A + rowmap_off(g.amap, m) + chunk * 8) : nullptr;
+            rowp[i] = (m < g.M) ? (g.A + rowmap_off(g.amap, m) + (size_t)kb_off * kBK + chunk * 8) : nullptr;
         }
         // software pipeline over a ring of kPF register buffers: the loads of k-blocks kb+1..kb+kPF-1 are
         // in flight while kb is split and stored (one L2/HBM round trip is ~1 us, a k-block of MMA far less).
@@ -342,9 +343,11 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                 if (lane == 0) mbar_arrive(full_bar(s));
             }
         } else {
+        if (dbg && tid == 0) dbg[7] = clock64();           // row pointers ready, first loads about to issue
 #pragma unroll
         for (int j = 0; j < kPF - 1; ++j)
             if (j < nkb) load_a_rows(rowp, j, vr[j]);
+        if (dbg && tid == 0) dbg[8] = clock64();           // prefetch loads issued
         for (int kb0 = 0; kb0 < nkb; kb0 += kPF) {
 #pragma unroll
             for (int j = 0; j < kPF; ++j) {
@@ -354,10 +357,16 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                     const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
                     if (kb + kPF - 1 < nkb) load_a_rows(rowp, kb + kPF - 1, vr[(j + kPF - 1) % kPF]);
                     mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (dbg && tid == 0 && kb == 0) {
+                        asm volatile("" ::"f"(vr[0][3][1].w));   // wait for the last load of k-block 0
+                        dbg[9] = clock64();
+                    }
                     store_a_rows(vr[j], a_hi(s), a_lo(s), r0, chunk);
+                    if (dbg && tid == 0 && kb == 0) dbg[10] = clock64();
                     fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full_bar(s));
+                    if (dbg && tid == 0 && kb == 0) dbg[11] = clock64();
                 }
             }
         }
@@ -380,12 +389,17 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
         tc_fence_after();
         if (dbg && tid == 0) dbg[2] = clock64();          // accumulator complete, epilogue starts
         const uint32_t tm_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        GemmArgs ge = g;                                  // split-K: partial z goes to its own slab, bias only in slab 0
+        if (g.ksplit > 1) {
+            ge.C = g.C + (size_t)blockIdx.z * g.csplit_stride;
+            if (blockIdx.z != 0) ge.bias = nullptr;
+        }
         if (g.R) {
-            if (g.act == 1) epilogue_chunks<kChunks, true, true>(g, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
-            else epilogue_chunks<kChunks, true, false>(g, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+            if (g.act == 1) epilogue_chunks<kChunks, true, true>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+            else epilogue_chunks<kChunks, true, false>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
         } else {
-            if (g.act == 1) epilogue_chunks<kChunks, false, true>(g, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
-            else epilogue_chunks<kChunks, false, false>(g, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+            if (g.act == 1) epilogue_chunks<kChunks, false, true>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+            else epilogue_chunks<kChunks, false, false>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
         }
         if (dbg && tid == 0) dbg[3] = clock64();          // epilogue of warp 0 done
     } else if (warp == kProducerWarps) {
@@ -396,8 +410,8 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                 const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 mbar_arrive_expect_tx(full_bar(s), 2u * C::kWTile);
-                tma_load_2d(w_hi(s), &map_hi, kb * kBK, n0, full_bar(s));
-                tma_load_2d(w_lo(s), &map_lo, kb * kBK, n0, full_bar(s));
+                tma_load_2d(w_hi(s), &map_hi, (kb_off + kb) * kBK, n0, full_bar(s));
+                tma_load_2d(w_lo(s), &map_lo, (kb_off + kb) * kBK, n0, full_bar(s));
             }
             if (dbg) dbg[6] = clock64();              // last TMA issued
         }
@@ -741,6 +755,7 @@ int pick_tile(const GemmArgs& g, const TcWeight& w, int force_bn) {
     if (force_bn)
         for (int t = 0; t < 3; ++t)
             if (kTileN[t] == force_bn && w.has_tile[t]) return t;
+    if (g.ksplit > 1 && w.has_tile[0]) return 0;       // split-K problems are small: 64-wide tiles
     int sms = 148;
     int best = -1;
     long best_cost = 0;
@@ -757,6 +772,18 @@ int pick_tile(const GemmArgs& g, const TcWeight& w, int force_bn) {
     return best < 0 ? 1 : best;
 }
 
+// Split-K factor for small problems with a long K (conv3/4, downsample): as many K slices as keep the
+// launch within one wave, at least 2 k-blocks per slice.
+int tc_pick_ksplit(int M, int N, int K, int max_split) {
+    const int mt = (M + kBM - 1) / kBM, nt = N / 64, nkb = K / kBK;
+    int best = 1;
+    for (int ks = 1; ks <= max_split && ks <= nkb; ++ks) {
+        if (nkb % ks != 0 || nkb / ks < 2) continue;
+        if (mt * nt * ks <= 148) best = ks;
+    }
+    return best;
+}
+
 // Resident-A path: number of N splits (grid.y) for the K = 256 kernel, 0 if it does not apply.
 int pick_k256_split(const GemmArgs& g) {
     if (g.K != 256 || g.N % 64 != 0) return 0;
@@ -771,7 +798,7 @@ int pick_k256_split(const GemmArgs& g) {
 }
 
 int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace& ws, cudaStream_t st) {
-    if (ws.use_k256 && ws.force_bn == 0) {
+    if (ws.use_k256 && ws.force_bn == 0 && g.ksplit == 1) {
         const int split = pick_k256_split(g);
         if (split > 0 && w.has_tile[0]) {
             const int ns = g.N / 64 / split;
@@ -784,7 +811,7 @@ int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace& ws, cudaSt
         }
     }
     const int t = pick_tile(g, w, ws.force_bn);
-    dim3 grid((g.M + kBM - 1) / kBM, g.N / kTileN[t]);
+    dim3 grid((g.M + kBM - 1) / kBM, g.N / kTileN[t], g.ksplit);
     const bool ln = g.ln_w != nullptr && g.K == 256;
 #define VAPB_LAUNCH_TC(BN_)                                                                                         \
     do {                                                                                                            \
@@ -821,6 +848,7 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
         {6400, 768, 256, 0, 0, 0, 0, 0},     // 11: QKV shape, no LN
         {128 * 56, 256, 2048, 1, 1, 0, 0, 0},// 12: conv1 at B=64
         {128, 256, 1280, 0, 1, 0, 0, 0},     // 13: downsample at B=64
+        {896, 256, 1024, 0, 1, 0, 0, 0},     // 14: conv4 at B=64 (run with split-K 4, partials summed on the host)
     };
     const int ncases = (int)(sizeof(cases) / sizeof(cases[0]));
     if (variant < 0 || variant >= ncases) {
@@ -869,6 +897,7 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
     TcWeight tw;
     std::string err, timing_note;
     int rc = 0;
+    float* dPartHost = nullptr;
     if (!tc_prepare_weight(dW, N, K, tw, allocs, err)) {
         report = err;
         rc = -3;
@@ -891,6 +920,15 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
             launch_sgemm(g, 0);
         }
         g.C = dC1;
+        const int ksplit = (variant == 14) ? 4 : 1;
+        float* dPart = nullptr;
+        if (ksplit > 1) {
+            al(&dPart, hR.size() * ksplit);
+            dPartHost = dPart;
+            g.C = dPart;
+            g.ksplit = ksplit;
+            g.csplit_stride = (long long)hR.size();
+        }
         TcWorkspace ws;
         ws.force_bn = force_bn;
         launch_gemm_tc(g, tw, ws, 0);
@@ -899,9 +937,9 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
             // timing (L2-warm, 20 back-to-back launches) + clock64 phase stamps of CTA (0,0)
             long long* ddbg = nullptr;
             const size_t nct = (size_t)((M + 127) / 128) * (N / 64);
-            cudaMalloc(reinterpret_cast<void**>(&ddbg), nct * 8 * sizeof(long long));
+            cudaMalloc(reinterpret_cast<void**>(&ddbg), nct * 16 * sizeof(long long));
             allocs.push_back(ddbg);
-            cudaMemset(ddbg, 0, nct * 8 * sizeof(long long));
+            cudaMemset(ddbg, 0, nct * 16 * sizeof(long long));
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
@@ -915,11 +953,12 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
             launch_gemm_tc(g, tw, ws, 0);
             g.dbg = nullptr;
             e = cudaDeviceSynchronize();
-            long long st[8];
+            long long st[16];
             cudaMemcpy(st, ddbg, sizeof st, cudaMemcpyDeviceToHost);
-            char tb[256];
-            snprintf(tb, sizeof tb, " | %.2f us/launch warm; CTA0 cycles: produced %lld, first_full %lld, last_mma_issue %lld, last_tma %lld, accum_ready %lld, epi_done %lld",
-                     ms * 1000.f / 20.f, st[1] - st[0], st[4] - st[0], st[5] - st[0], st[6] - st[0], st[2] - st[0], st[3] - st[0]);
+            char tb[400];
+            snprintf(tb, sizeof tb, " | %.2f us/launch warm; CTA0 cycles: ptrs %lld, loads_issued %lld, data0 %lld, stored0 %lld, arrived0 %lld, first_full %lld, produced %lld, last_mma_issue %lld, last_tma %lld, accum_ready %lld, epi_done %lld",
+                     ms * 1000.f / 20.f, st[7] - st[0], st[8] - st[0], st[9] - st[0], st[10] - st[0], st[11] - st[0], st[4] - st[0],
+                     st[1] - st[0], st[5] - st[0], st[6] - st[0], st[2] - st[0], st[3] - st[0]);
             timing_note = tb;
             cudaEventDestroy(e0);
             cudaEventDestroy(e1);
@@ -932,7 +971,14 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
     if (!rc) {
         std::vector<float> c0(hR.size()), c1(hR.size());
         cudaMemcpy(c0.data(), dC0, c0.size() * 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(c1.data(), dC1, c1.size() * 4, cudaMemcpyDeviceToHost);
+        if (variant == 14) {
+            std::vector<float> part(hR.size() * 4);
+            cudaMemcpy(part.data(), dPartHost, part.size() * 4, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < c1.size(); ++i)
+                c1[i] = part[i] + part[i + c1.size()] + part[i + 2 * c1.size()] + part[i + 3 * c1.size()];
+        } else {
+            cudaMemcpy(c1.data(), dC1, c1.size() * 4, cudaMemcpyDeviceToHost);
+        }
         double maxabs = 0, maxdiff = 0;
         size_t worst = 0, nbad = 0;
         for (size_t i = 0; i < c0.size(); ++i) {

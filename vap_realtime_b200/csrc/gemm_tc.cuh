@@ -41,6 +41,8 @@ struct TcWorkspace {
 bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vector<void*>& allocs, std::string& err);
 bool tc_prepare_workspace(TcWorkspace& ws, size_t max_a_elems, std::vector<void*>& allocs, std::string& err);
 
+int tc_pick_ksplit(int M, int N, int K, int max_split);
+
 // Enqueues the GEMM; returns the number of kernels launched.
 int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace& ws, cudaStream_t st);
 

@@ -321,8 +321,10 @@ __device__ __forceinline__ void warp_norm8(float v[8], float denom_inv, const fl
     for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * ww[i] + bb[i];
 }
 
+// With split-K partials ([nsplit][M][256], plain layout) the rows are summed here first.
 __global__ void __launch_bounds__(256) k_cn_relu(float* X, RowMap map, int M, const float* __restrict__ w,
-                                                 const float* __restrict__ b) {
+                                                 const float* __restrict__ b, const float* __restrict__ partials, int nsplit,
+                                                 long long split_stride) {
     pdl_trigger();
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -330,14 +332,25 @@ __global__ void __launch_bounds__(256) k_cn_relu(float* X, RowMap map, int M, co
     const int lane = threadIdx.x & 31;
     float* p = X + rowmap_off(map, row);
     float v[8];
-    load_row8(p, lane, v);
+    if (nsplit > 0) {
+        load_row8(partials + (size_t)row * kD, lane, v);
+        for (int z = 1; z < nsplit; ++z) {
+            float u[8];
+            load_row8(partials + (size_t)z * split_stride + (size_t)row * kD, lane, u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += u[i];
+        }
+    } else {
+        load_row8(p, lane, v);
+    }
     warp_norm8(v, 1.0f / 255.0f, w, b, lane);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
     store_row8(p, lane, v);
 }
-void launch_cn_relu(float* X, RowMap map, int M, const float* w, const float* b, cudaStream_t st) {
-    launch_k(k_cn_relu, dim3((M + 7) / 8), dim3(256), 0, st, X, map, M, w, b);
+void launch_cn_relu(float* X, RowMap map, int M, const float* w, const float* b, cudaStream_t st, const float* partials,
+                    int nsplit, long long split_stride) {
+    launch_k(k_cn_relu, dim3((M + 7) / 8), dim3(256), 0, st, X, map, M, w, b, partials, nsplit, split_stride);
 }
 
 __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ X, RowMap xmap, float* __restrict__ Y,
@@ -596,7 +609,7 @@ void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* 
 __global__ void __launch_bounds__(256) k_ln_gelu_ring(const float* __restrict__ X, int B, const float* __restrict__ w,
                                                       const float* __restrict__ b, float* ring,
                                                       const int* __restrict__ count, const int* __restrict__ ids,
-                                                      int T, float* e_out) {
+                                                      int T, float* e_out, int nsplit, long long split_stride) {
     pdl_trigger();
     pdl_wait();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -604,6 +617,12 @@ __global__ void __launch_bounds__(256) k_ln_gelu_ring(const float* __restrict__ 
     const int lane = threadIdx.x & 31;
     float v[8];
     load_row8(X + (size_t)n * kD, lane, v);
+    for (int z = 1; z < nsplit; ++z) {          // split-K partials of the downsample GEMM
+        float u[8];
+        load_row8(X + (size_t)z * split_stride + (size_t)n * kD, lane, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += u[i];
+    }
     warp_norm8(v, 1.0f / 256.0f, w, b, lane);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
@@ -613,8 +632,9 @@ __global__ void __launch_bounds__(256) k_ln_gelu_ring(const float* __restrict__ 
     if (e_out) store_row8(e_out + (size_t)n * kD, lane, v);
 }
 void launch_ln_gelu_ring(const float* X, int B, const float* w, const float* b, float* ring, const int* count,
-                         const int* ids, int T, float* e_out, cudaStream_t st) {
-    launch_k(k_ln_gelu_ring, dim3((2 * B + 7) / 8), dim3(256), 0, st, X, B, w, b, ring, count, ids, T, e_out);
+                         const int* ids, int T, float* e_out, cudaStream_t st, int nsplit, long long split_stride) {
+    launch_k(k_ln_gelu_ring, dim3((2 * B + 7) / 8), dim3(256), 0, st, X, B, w, b, ring, count, ids, T, e_out, nsplit,
+             split_stride);
 }
 
 // X[(n*T + j)] = ring row of logical position j (oldest first) for j < t, zero rows above.
