@@ -122,19 +122,22 @@ def test_offline_golden_head(vap_weights):
     assert np.abs(out[:, :4] - rows[:, 1:]).max() < 1e-4
 
 
-def test_offline_golden_full(vap_weights):
-    """All 5312 rows of output_offline.txt through the tensor-core path."""
+@pytest.mark.parametrize("conv4p", [1, 0])
+def test_offline_golden_full(vap_weights, conv4p):
+    """All 5312 rows of output_offline.txt through the tensor-core path (conv4p: with / without the
+    lo*lo product in the conv stack)."""
     d = np.load(built_asset("jpn_pair_16k.npz"))
     g = np.load(built_asset("golden_offline.npy"))
     audio = torch.from_numpy(np.stack([d["left"], d["right"]]).astype(np.float32) / 32768.0).cuda()
     eng = VapEngine(vap_weights, 20, 50, max_streams=1)
     eng.set_option("gemm", DEF)
+    eng.set_option("conv4p", conv4p)
     outs = torch.empty((len(g), 6), device="cuda")
     for n in range(len(g)):
         eng.step(audio[None, :, 800 * n: 800 * n + 1120].contiguous(), out=outs[n:n + 1])
     out = outs.cpu().numpy()
     d = np.abs(out[:, :4] - g[:, 1:])
-    print("golden file: max|d| =", d.max(), "frames > 1e-5:", int((d.max(1) > 1e-5).sum()))
+    print(f"golden file (conv4p={conv4p}): max|d| =", d.max(), "frames > 1e-5:", int((d.max(1) > 1e-5).sum()))
     assert d.max() < 1e-4
 
 

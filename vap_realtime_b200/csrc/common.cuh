@@ -59,6 +59,9 @@ struct GemmArgs {
     // C + z * csplit_stride (no activation / residual; bias only in partial 0); the consumer sums them.
     int ksplit = 1;
     long long csplit_stride = 0;
+    // 1: also accumulate the lo*lo product (4 MMAs per k-step).  Used for the conv stack, whose rounding
+    // is amplified by the ChannelNorms and dominates the end-to-end error (precision).
+    int four_products = 0;
 };
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------
@@ -66,14 +69,38 @@ struct GemmArgs {
 // prologue: barrier init, TMEM allocation, tensor-map prefetch, weight TMA) and pdl_wait() before it
 // touches anything a previous kernel produced.  Both are no-ops for a normal launch.
 #ifdef __CUDACC__
+#ifdef VAPB_ENABLE_PDL
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+// PDL measured slower than plain graph edges on this driver (profiles/r01_*_option_ablation.log) and
+// griddepcontrol.wait costs ~1k cycles even on a normal launch, so it is compiled out by default.
+__device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_wait() {}
+#endif
 
 extern bool g_use_pdl;      // set by the step driver before it enqueues kernels
 extern bool g_attn_rk;
 
+// All kernels of the step ask for the same (maximum) shared-memory carve-out, so the SMs never have to
+// re-partition L1 / shared memory between a 197 KB GEMM and a small row-wise kernel.
+template <typename... KArgs>
+inline void prefer_max_smem(void (*kernel)(KArgs...)) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    {   // once per kernel function
+        static const void* seen[64];
+        static int n_seen = 0;
+        bool found = false;
+        for (int i = 0; i < n_seen; ++i) found = found || (seen[i] == reinterpret_cast<const void*>(kernel));
+        if (!found) {
+            prefer_max_smem(kernel);
+            if (n_seen < 64) seen[n_seen++] = reinterpret_cast<const void*>(kernel);
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -83,7 +110,11 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
+#ifdef VAPB_ENABLE_PDL
     cfg.numAttrs = g_use_pdl ? 1 : 0;
+#else
+    cfg.numAttrs = 0;
+#endif
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

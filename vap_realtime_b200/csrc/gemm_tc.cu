@@ -183,13 +183,20 @@ __device__ __forceinline__ void store_a_rows(const float4 (&v)[4][2], uint32_t a
 // block are in flight before the first one is consumed.
 template <int kChunks, bool HAS_R, bool GELU>
 __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tm_row, float* tbuf, int n_base, int tm_col0,
-                                                int lane, int rows_valid, long long coff_own, long long roff_own) {
+                                                int lane, int rows_valid, long long coff_own, long long roff_own,
+                                                uint32_t small_off = 0) {
     const int sub = lane >> 3;        // row within a group of 4
     const int c4 = (lane & 7) * 4;    // first of this lane's 4 columns
 #pragma unroll 1
     for (int cb = 0; cb < kChunks; ++cb) {
         uint32_t raw[32];
         tmem_ld32(tm_row + (uint32_t)(tm_col0 + cb * 32), raw);
+        if (small_off) {          // second accumulator holding the small (lo) products: summed here in fp32
+            uint32_t raw2[32];
+            tmem_ld32(tm_row + small_off + (uint32_t)(tm_col0 + cb * 32), raw2);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) raw[c] = __float_as_uint(__uint_as_float(raw[c]) + __uint_as_float(raw2[c]));
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(tbuf + lane * kEpiPitch + 4 * q) =
@@ -261,7 +268,12 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
         prefetch_tmap(&map_hi);
         prefetch_tmap(&map_lo);
     }
-    if (warp == kProducerWarps + 1) tmem_alloc(tmem_slot, BN);
+    // "four_products" mode keeps two accumulators: hi*hi in columns [0, BN), the three small products in
+    // [BN, 2 BN).  The tensor core aligns addends to the accumulator's exponent, so small terms added to a
+    // large running sum lose bits; kept apart and summed in fp32 by the epilogue they do not.
+    const uint32_t small_off = (g.four_products && BN <= 128) ? (uint32_t)BN : 0u;
+    const uint32_t tmem_cols = small_off ? 2u * BN : (uint32_t)BN;
+    if (warp == kProducerWarps + 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -395,11 +407,11 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
             if (blockIdx.z != 0) ge.bias = nullptr;
         }
         if (g.R) {
-            if (g.act == 1) epilogue_chunks<kChunks, true, true>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
-            else epilogue_chunks<kChunks, true, false>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+            if (g.act == 1) epilogue_chunks<kChunks, true, true>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own, small_off);
+            else epilogue_chunks<kChunks, true, false>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own, small_off);
         } else {
-            if (g.act == 1) epilogue_chunks<kChunks, false, true>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
-            else epilogue_chunks<kChunks, false, false>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own);
+            if (g.act == 1) epilogue_chunks<kChunks, false, true>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own, small_off);
+            else epilogue_chunks<kChunks, false, false>(ge, tm_row, tbuf, n0 + half * (BN / 2), half * (BN / 2), lane, rows_valid, coff_own, roff_own, small_off);
         }
         if (dbg && tid == 0) dbg[3] = clock64();          // epilogue of warp 0 done
     } else if (warp == kProducerWarps) {
@@ -430,9 +442,17 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                     const uint32_t koff = (uint32_t)k * kUmmaK * 2;          // bytes along K inside the swizzle row
                     const uint64_t ah = make_desc(a_hi(s) + koff), al = make_desc(a_lo(s) + koff);
                     const uint64_t wh = make_desc(w_hi(s) + koff), wl = make_desc(w_lo(s) + koff);
-                    umma_bf16(tmem_base, al, wh, idesc, (kb | k) ? 1u : 0u);   // small terms first
-                    umma_bf16(tmem_base, ah, wl, idesc, 1u);
-                    umma_bf16(tmem_base, ah, wh, idesc, 1u);
+                    const uint32_t first = (kb | k) ? 1u : 0u;
+                    if (g.four_products) {
+                        umma_bf16(tmem_base + small_off, al, wl, idesc, first);     // smallest term first
+                        umma_bf16(tmem_base + small_off, al, wh, idesc, 1u);
+                        umma_bf16(tmem_base + small_off, ah, wl, idesc, 1u);
+                        umma_bf16(tmem_base, ah, wh, idesc, small_off ? first : 1u);
+                    } else {
+                        umma_bf16(tmem_base, al, wh, idesc, first);                 // small terms first
+                        umma_bf16(tmem_base, ah, wl, idesc, 1u);
+                        umma_bf16(tmem_base, ah, wh, idesc, 1u);
+                    }
                 }
                 umma_commit(empty_bar(s));            // frees the stage when these MMAs have read it
             }
@@ -442,7 +462,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kProducerWarps + 1) tmem_dealloc(tmem_base, BN);
+    if (warp == kProducerWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ---- K = 256 kernel: A resident in shared memory, loop over N ------------------------------------
@@ -756,10 +776,11 @@ int pick_tile(const GemmArgs& g, const TcWeight& w, int force_bn) {
         for (int t = 0; t < 3; ++t)
             if (kTileN[t] == force_bn && w.has_tile[t]) return t;
     if (g.ksplit > 1 && w.has_tile[0]) return 0;       // split-K problems are small: 64-wide tiles
+    const int tmax = g.four_products ? 1 : 2;          // two-accumulator mode: N tile <= 128
     int sms = 148;
     int best = -1;
     long best_cost = 0;
-    for (int t = 2; t >= 0; --t) {
+    for (int t = tmax; t >= 0; --t) {
         if (!w.has_tile[t]) continue;
         const long ctas = (long)mt * (g.N / kTileN[t]);
         const long waves = (ctas + sms - 1) / sms;
@@ -929,8 +950,9 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
             g.ksplit = ksplit;
             g.csplit_stride = (long long)hR.size();
         }
+        if (cs.conv) g.four_products = 1;
         TcWorkspace ws;
-        ws.force_bn = force_bn;
+        ws.force_bn = (cs.conv && force_bn == 256) ? 128 : force_bn;
         launch_gemm_tc(g, tw, ws, 0);
         cudaError_t e = cudaDeviceSynchronize();
         if (e == cudaSuccess) {

@@ -118,7 +118,7 @@ struct vapb_ctx {
     int last_B = 0;
 
     // options
-    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_prune = 1, opt_attn_rk = 0, opt_fork = 0, opt_splitk = 1, opt_pdl = 0;   // attn_rk / fork / pdl measured no better (profiles/r01_h_option_ablation.log)   // PDL measured slower inside CUDA graphs on this driver (ablation in profiles/)
+    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_prune = 1, opt_attn_rk = 0, opt_fork = 0, opt_splitk = 1, opt_conv4p = 1, opt_pdl = 0;   // attn_rk / fork / pdl measured no better (profiles/r01_h_option_ablation.log)   // PDL measured slower inside CUDA graphs on this driver (ablation in profiles/)
     std::vector<GraphEntry> graphs;
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -327,10 +327,11 @@ void mark(Step& s, const char* tag, int launches = 1) {
 // C = act(A W^T + bias) + R through the selected GEMM engine.
 void gemm(Step& s, const char* tag, const float* A, RowMap amap, const float* W, const TcWeight* tcw, const float* bias,
           const float* R, RowMap rmap, float* C, RowMap cmap, int M, int N, int K, int act, const float* ln_w = nullptr,
-          const float* ln_b = nullptr, int ksplit = 1, long long csplit_stride = 0) {
+          const float* ln_b = nullptr, int ksplit = 1, long long csplit_stride = 0, int four_products = 0) {
     GemmArgs g;
     g.ln_w = ln_w; g.ln_b = ln_b;
     g.ksplit = ksplit; g.csplit_stride = csplit_stride;
+    g.four_products = four_products;
     g.A = A; g.amap = amap; g.W = W; g.bias = bias; g.R = R; g.rmap = rmap; g.C = C; g.cmap = cmap;
     g.M = M; g.N = N; g.K = K; g.act = act;
     if (s.c->opt_gemm == 1 && tcw && tcw->hi) {
@@ -467,14 +468,18 @@ void enqueue_step(Step& s) {
         am.offset = (long long)(c->halo[i] - cv.p) * kD;
         const RowMap cm = act_map(c, i + 1);
         const int Mc = NC * cv.Lout;
-        const int ks = (c->opt_gemm == 1 && c->opt_splitk && (size_t)Mc * kD <= c->part_stride) ? tc_pick_ksplit(Mc, kD, cv.k * kD, 16) : 1;
+        // split-K factors are fixed per layer (conv3: 2, conv4: 4) so that a stream's arithmetic does not depend
+        // on the batch size; shorter accumulation chains + fp32 summation also measurably help parity
+        const int ks_layer[4] = {1, 1, 2, 4};
+        const int ks = (c->opt_gemm == 1 && c->opt_splitk && (size_t)Mc * kD <= c->part_stride) ? ks_layer[i] : 1;
         if (ks > 1) {
             // small M, long K: K is split over CTAs; ChannelNorm sums the partial products
             gemm(s, "gemm_conv_splitk", c->act[i], am, cv.W, &cv.tc, cv.b, nullptr, cm, c->part, plain_map(kD), Mc, kD, cv.k * kD, 0,
-                 nullptr, nullptr, ks, (long long)c->part_stride);
+                 nullptr, nullptr, ks, (long long)c->part_stride, c->opt_conv4p);
             launch_cn_relu(c->act[i + 1], cm, Mc, cv.cnw, cv.cnb, st, c->part, ks, (long long)c->part_stride); mark(s, "cn_relu");
         } else {
-            gemm(s, i == 0 ? "gemm_conv1" : "gemm_conv2_4", c->act[i], am, cv.W, &cv.tc, cv.b, nullptr, cm, c->act[i + 1], cm, Mc, kD, cv.k * kD, 0);
+            gemm(s, i == 0 ? "gemm_conv1" : "gemm_conv2_4", c->act[i], am, cv.W, &cv.tc, cv.b, nullptr, cm, c->act[i + 1], cm, Mc, kD, cv.k * kD, 0,
+                 nullptr, nullptr, 1, 0, c->opt_conv4p);
             launch_cn_relu(c->act[i + 1], cm, Mc, cv.cnw, cv.cnb, st); mark(s, "cn_relu");
         }
     }
@@ -507,11 +512,12 @@ void enqueue_step(Step& s) {
     // ---- downsample conv over exactly n_lstm frames + LayerNorm + GELU -> ring
     {
         const int Kd = c->n_lstm * kD;
-        const int ks = (c->opt_gemm == 1 && c->opt_splitk) ? tc_pick_ksplit(NC, kD, Kd, 16) : 1;
+        const int ks = (c->opt_gemm == 1 && c->opt_splitk) ? (Kd / 64) / 2 : 1;      // 2 k-blocks per slice, any batch
         if (ks > 1) {
+            const long long dstride = (long long)NC * kD;
             gemm(s, "gemm_downsample", c->Y, plain_map(Kd), c->Wds, &c->tc_ds, c->bds, nullptr, plain_map(kD), c->part, plain_map(kD), NC, kD, Kd, 0,
-                 nullptr, nullptr, ks, (long long)c->part_stride);
-            launch_ln_gelu_ring(c->part, B, c->ds_lnw, c->ds_lnb, c->ring, c->count, c->ids_dev, T, c->ebuf, st, ks, (long long)c->part_stride);
+                 nullptr, nullptr, ks, dstride, c->opt_conv4p);
+            launch_ln_gelu_ring(c->part, B, c->ds_lnw, c->ds_lnb, c->ring, c->count, c->ids_dev, T, c->ebuf, st, ks, dstride);
         } else {
             gemm(s, "gemm_downsample", c->Y, plain_map(Kd), c->Wds, &c->tc_ds, c->bds, nullptr, plain_map(kD), c->dsout, plain_map(kD), NC, kD, Kd, 0);
             launch_ln_gelu_ring(c->dsout, B, c->ds_lnw, c->ds_lnb, c->ring, c->count, c->ids_dev, T, c->ebuf, st);
@@ -696,7 +702,7 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     DA(c->KVc, R * 2 * kD);
     DA(c->Qc, R * kD);
     c->part_stride = NC * (size_t)c->L[3] * kD;          // largest split-K user: conv3 output rows
-    DA(c->part, 16 * c->part_stride);
+    DA(c->part, 4 * c->part_stride + 20 * NC * kD);      // conv3/conv4 use <= 4 slabs; the downsample up to 20 tiny ones
     DA(c->Xl, NC * kD);
     DA(c->Zl, NC * kD);
     DA(c->Ql, NC * kD);
@@ -937,7 +943,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -951,6 +957,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "attn_rk") h->opt_attn_rk = value ? 1 : 0;
         else if (k == "fork") h->opt_fork = value ? 1 : 0;
         else if (k == "splitk") h->opt_splitk = value ? 1 : 0;
+        else if (k == "conv4p") h->opt_conv4p = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -983,6 +990,7 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "attn_rk") *value = h->opt_attn_rk;
     else if (k == "fork") *value = h->opt_fork;
     else if (k == "splitk") *value = h->opt_splitk;
+    else if (k == "conv4p") *value = h->opt_conv4p;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
