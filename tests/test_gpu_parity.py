@@ -122,7 +122,7 @@ def test_offline_golden_head(vap_weights):
     assert np.abs(out[:, :4] - rows[:, 1:]).max() < 1e-4
 
 
-@pytest.mark.parametrize("conv4p", [1, 0])
+@pytest.mark.parametrize("conv4p", [1, 3, 0])
 def test_offline_golden_full(vap_weights, conv4p):
     """All 5312 rows of output_offline.txt through the tensor-core path (conv4p: with / without the
     lo*lo product in the conv stack)."""
@@ -191,7 +191,8 @@ def test_option_variants_agree(vap_weights, fixture_audio):
         assert np.abs(outs[name][:, 0] - ref[:70]).max() < TOL[DEF]
     for name in outs:
         assert np.abs(outs[name] - outs["default"]).max() < 2e-5, name
-    assert np.array_equal(outs["tile64"], outs["tile256"])        # tile width does not change a row's arithmetic
+    assert np.array_equal(outs["tile64"], outs["tile128"])        # tile width does not change a row's arithmetic
+    # (256-wide tiles leave no TMEM room for the conv stack's second accumulator, so they differ at the 1e-5 level)
 
 
 def test_graph_equals_eager(vap_weights, fixture_audio):

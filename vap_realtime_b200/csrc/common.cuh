@@ -59,8 +59,11 @@ struct GemmArgs {
     // C + z * csplit_stride (no activation / residual; bias only in partial 0); the consumer sums them.
     int ksplit = 1;
     long long csplit_stride = 0;
-    // 1: also accumulate the lo*lo product (4 MMAs per k-step).  Used for the conv stack, whose rounding
-    // is amplified by the ChannelNorms and dominates the end-to-end error (precision).
+    // Extra-precision modes of the generic tcgen05 kernel, used for the conv stack whose rounding is
+    // amplified by the ChannelNorms and dominates the end-to-end error (precision):
+    //   bit 0: keep the small products (hi*lo, lo*hi[, lo*lo]) in a second TMEM accumulator and add it to
+    //          the hi*hi accumulator in fp32 in the epilogue (no extra MMA);
+    //   bit 1: also issue the lo*lo product (4 MMAs per k-step instead of 3).
     int four_products = 0;
 };
 
@@ -82,25 +85,10 @@ __device__ __forceinline__ void pdl_wait() {}
 extern bool g_use_pdl;      // set by the step driver before it enqueues kernels
 extern bool g_attn_rk;
 
-// All kernels of the step ask for the same (maximum) shared-memory carve-out, so the SMs never have to
-// re-partition L1 / shared memory between a 197 KB GEMM and a small row-wise kernel.
-template <typename... KArgs>
-inline void prefer_max_smem(void (*kernel)(KArgs...)) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
-
+// (A uniform max-shared-memory carve-out hint for every kernel was tried and measured ~5 % slower:
+//  the row-wise kernels lose their L1.  profiles/r01_j_option_ablation.log)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    {   // once per kernel function
-        static const void* seen[64];
-        static int n_seen = 0;
-        bool found = false;
-        for (int i = 0; i < n_seen; ++i) found = found || (seen[i] == reinterpret_cast<const void*>(kernel));
-        if (!found) {
-            prefer_max_smem(kernel);
-            if (n_seen < 64) seen[n_seen++] = reinterpret_cast<const void*>(kernel);
-        }
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;

@@ -271,7 +271,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     // "four_products" mode keeps two accumulators: hi*hi in columns [0, BN), the three small products in
     // [BN, 2 BN).  The tensor core aligns addends to the accumulator's exponent, so small terms added to a
     // large running sum lose bits; kept apart and summed in fp32 by the epilogue they do not.
-    const uint32_t small_off = (g.four_products && BN <= 128) ? (uint32_t)BN : 0u;
+    const uint32_t small_off = ((g.four_products & 1) && BN <= 128) ? (uint32_t)BN : 0u;
     const uint32_t tmem_cols = small_off ? 2u * BN : (uint32_t)BN;
     if (warp == kProducerWarps + 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
@@ -444,8 +444,12 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                     const uint64_t wh = make_desc(w_hi(s) + koff), wl = make_desc(w_lo(s) + koff);
                     const uint32_t first = (kb | k) ? 1u : 0u;
                     if (g.four_products) {
-                        umma_bf16(tmem_base + small_off, al, wl, idesc, first);     // smallest term first
-                        umma_bf16(tmem_base + small_off, al, wh, idesc, 1u);
+                        if (g.four_products & 2) {
+                            umma_bf16(tmem_base + small_off, al, wl, idesc, first);     // smallest term first
+                            umma_bf16(tmem_base + small_off, al, wh, idesc, 1u);
+                        } else {
+                            umma_bf16(tmem_base + small_off, al, wh, idesc, first);
+                        }
                         umma_bf16(tmem_base + small_off, ah, wl, idesc, 1u);
                         umma_bf16(tmem_base, ah, wh, idesc, small_off ? first : 1u);
                     } else {
@@ -776,7 +780,7 @@ int pick_tile(const GemmArgs& g, const TcWeight& w, int force_bn) {
         for (int t = 0; t < 3; ++t)
             if (kTileN[t] == force_bn && w.has_tile[t]) return t;
     if (g.ksplit > 1 && w.has_tile[0]) return 0;       // split-K problems are small: 64-wide tiles
-    const int tmax = g.four_products ? 1 : 2;          // two-accumulator mode: N tile <= 128
+    const int tmax = (g.four_products & 1) ? 1 : 2;    // two-accumulator mode: N tile <= 128
     int sms = 148;
     int best = -1;
     long best_cost = 0;
@@ -950,7 +954,7 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
             g.ksplit = ksplit;
             g.csplit_stride = (long long)hR.size();
         }
-        if (cs.conv) g.four_products = 1;
+        if (cs.conv) g.four_products = 3;
         TcWorkspace ws;
         ws.force_bn = (cs.conv && force_bn == 256) ? 128 : force_bn;
         launch_gemm_tc(g, tw, ws, 0);

@@ -118,7 +118,7 @@ struct vapb_ctx {
     int last_B = 0;
 
     // options
-    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_prune = 1, opt_attn_rk = 0, opt_fork = 0, opt_splitk = 1, opt_conv4p = 1, opt_pdl = 0;   // attn_rk / fork / pdl measured no better (profiles/r01_h_option_ablation.log)   // PDL measured slower inside CUDA graphs on this driver (ablation in profiles/)
+    int opt_graph = 1, opt_gemm = 0, opt_keep_taps = 0, opt_timing = 0, opt_lstm_fused = 1, opt_tile_n = 0, opt_fuse_ln = 1, opt_prune = 1, opt_attn_rk = 0, opt_fork = 0, opt_splitk = 1, opt_conv4p = 1, opt_pdl = 0;   // conv4p: 1 = two accumulators, 3 = + lo*lo product   // attn_rk / fork / pdl measured no better (profiles/r01_h_option_ablation.log)   // PDL measured slower inside CUDA graphs on this driver (ablation in profiles/)
     std::vector<GraphEntry> graphs;
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -957,7 +957,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "attn_rk") h->opt_attn_rk = value ? 1 : 0;
         else if (k == "fork") h->opt_fork = value ? 1 : 0;
         else if (k == "splitk") h->opt_splitk = value ? 1 : 0;
-        else if (k == "conv4p") h->opt_conv4p = value ? 1 : 0;
+        else if (k == "conv4p") h->opt_conv4p = value & 3;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
