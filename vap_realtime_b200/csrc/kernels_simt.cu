@@ -528,7 +528,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
         float acc[RH];
 #pragma unroll
         for (int r = 0; r < RH; ++r) acc[r] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
         for (int k = 0; k < kD; k += 4) {
             const float w0 = sW[(k + 0) * kLstmWPitch + col], w1 = sW[(k + 1) * kLstmWPitch + col];
             const float w2 = sW[(k + 2) * kLstmWPitch + col], w3 = sW[(k + 3) * kLstmWPitch + col];
