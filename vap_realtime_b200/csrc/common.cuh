@@ -82,6 +82,19 @@ __device__ __forceinline__ void pdl_trigger() {}
 __device__ __forceinline__ void pdl_wait() {}
 #endif
 
+// cudaFuncSetAttribute is per device: true the first time a given call site runs on the current device
+struct OncePerDevice {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 extern bool g_use_pdl;      // set by the step driver before it enqueues kernels
 extern bool g_attn_rk;
 

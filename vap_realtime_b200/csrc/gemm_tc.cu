@@ -752,8 +752,8 @@ constexpr int kTileN[3] = {64, 128, 256};
 
 template <int BN>
 bool ensure_attr(std::string* err) {
-    static bool done = false;
-    if (done) return true;
+    static OncePerDevice once;
+    if (!once.first()) return true;
     cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_gemm_tc<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
@@ -761,7 +761,6 @@ bool ensure_attr(std::string* err) {
         if (err) *err = std::string("cudaFuncSetAttribute(k_gemm_tc) failed: ") + cudaGetErrorString(e);
         return false;
     }
-    done = true;
     return true;
 }
 
@@ -800,15 +799,14 @@ bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vec
         if (!encode_plane(&out.map_lo[t], lo, N, K, kTileN[t], err)) return false;
     }
     if (!ensure_attr<64>(&err) || !ensure_attr<128>(&err) || !ensure_attr<256>(&err)) return false;
-    static bool k256_done = false;
-    if (!k256_done) {
+    static OncePerDevice k256_once;
+    if (k256_once.first()) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_tc_k256<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc_k256<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
         if (e != cudaSuccess) {
             err = std::string("cudaFuncSetAttribute(k_gemm_tc_k256) failed: ") + cudaGetErrorString(e);
             return false;
         }
-        k256_done = true;
     }
     return true;
 }

@@ -583,11 +583,10 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
 
 void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* cS, const int* ids, float* Y, int NC,
                            int n_steps, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice once;
+    if (once.first()) {
         cudaFuncSetAttribute(k_lstm_recurrent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<8>());
         cudaFuncSetAttribute(k_lstm_recurrent<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<16>());
-        attr_set = true;
     }
     // 8-row tiles while that still fits one wave of clusters (more SMs busy), 16-row tiles for big batches
     if ((NC + 7) / 8 * 8 <= 144) {
@@ -886,11 +885,8 @@ void launch_attention(const AttnArgs& a, cudaStream_t st) {
         return;
     }
     const size_t smem = (size_t)(((a.T * 65 + 3) & ~3) + a.T * 64 + kAttnWarps * 64 + kAttnWarps * 128) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-    }
+    static OncePerDevice once;
+    if (once.first()) cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     dim3 grid(a.n_seq, kHeads);
     launch_k(k_attention, grid, dim3(kAttnWarps * 32), smem, st, a);
 }
