@@ -234,37 +234,6 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, uint32_t tm_r
     }
 }
 
-// 8-row variants for the two-group producer of the generic kernel (rows r0 + 16*i of the tile)
-__device__ __forceinline__ void load_a_rows8(const float* const (&rowp)[8], int kb, float4 (&v)[8][2]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (rowp[i]) {
-            const float4* p = reinterpret_cast<const float4*>(rowp[i] + (size_t)kb * kBK);
-            v[i][0] = __ldg(p);
-            v[i][1] = __ldg(p + 1);
-        } else {
-            v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            v[i][1] = v[i][0];
-        }
-    }
-}
-__device__ __forceinline__ void store_a_rows8(const float4 (&v)[8][2], uint32_t a_hi, uint32_t a_lo, int r0, int chunk) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 16 * i;
-        uint32_t h[4], l[4];
-        split2(v[i][0].x, v[i][0].y, h[0], l[0]);
-        split2(v[i][0].z, v[i][0].w, h[1], l[1]);
-        split2(v[i][1].x, v[i][1].y, h[2], l[2]);
-        split2(v[i][1].z, v[i][1].w, h[3], l[3]);
-        const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(chunk ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
-                     : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3])
-                     : "memory");
-    }
-}
-
 template <int BN, bool LN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
@@ -291,8 +260,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
 
     if (warp == kProducerWarps && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) {
-            // LN prologue: all 8 producer warps fill every stage; otherwise the two warp groups alternate stages
-            mbar_init(full_bar(s), (LN ? kProducerWarps : kProducerWarps / 2) + 1);   // + the TMA thread's expect_tx arrive
+            mbar_init(full_bar(s), kProducerWarps + 1);   // producer warps + the TMA thread's expect_tx arrive
             mbar_init(empty_bar(s), 1);                   // one tcgen05.commit
         }
         mbar_init(bar_accum, 1);
@@ -387,44 +355,33 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
                 if (lane == 0) mbar_arrive(full_bar(s));
             }
         } else {
-            // Two warp groups alternate k-blocks.  The generic->async proxy fence after the smem stores is
-            // a MEMBAR that also waits for the group's outstanding global prefetch, so a single group
-            // would pay one L2 round trip per k-block; with two groups one converts while the other waits.
-            const int grp = warp >> 2, t128 = tid & 127;
-            const int chunk8 = t128 & 7, r0g = t128 >> 3;          // rows r0g + 16*i, i < 8
-            const float* rowp8[8];
+        if (dbg && tid == 0) dbg[7] = clock64();           // row pointers ready, first loads about to issue
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = m0 + r0g + 16 * i;
-                rowp8[i] = (m < g.M) ? (g.A + rowmap_off(g.amap, m) + (size_t)kb_off * kBK + chunk8 * 8) : nullptr;
-            }
-            if (dbg && tid == 0) dbg[7] = clock64();           // row pointers ready, first loads about to issue
-            float4 va8[8][2], vb8[8][2];
-            if (grp < nkb) load_a_rows8(rowp8, grp, va8);
-            if (dbg && tid == 0) dbg[8] = clock64();           // first loads issued
-            auto produce = [&](const float4 (&v)[8][2], int kb) {
-                const int s = kb % C::kStages;
-                const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                if (dbg && tid == 0 && kb == 0) {
-                    asm volatile("" ::"f"(v[7][1].w));
-                    dbg[9] = clock64();                        // data of k-block 0 arrived
-                }
-                store_a_rows8(v, a_hi(s), a_lo(s), r0g, chunk8);
-                if (dbg && tid == 0 && kb == 0) dbg[10] = clock64();
-                fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(s));
-                if (dbg && tid == 0 && kb == 0) dbg[11] = clock64();
-            };
-            for (int kb = grp; kb < nkb; kb += 4) {
-                if (kb + 2 < nkb) load_a_rows8(rowp8, kb + 2, vb8);
-                produce(va8, kb);
-                if (kb + 2 < nkb) {
-                    if (kb + 4 < nkb) load_a_rows8(rowp8, kb + 4, va8);
-                    produce(vb8, kb + 2);
+        for (int j = 0; j < kPF - 1; ++j)
+            if (j < nkb) load_a_rows(rowp, j, vr[j]);
+        if (dbg && tid == 0) dbg[8] = clock64();           // prefetch loads issued
+        for (int kb0 = 0; kb0 < nkb; kb0 += kPF) {
+#pragma unroll
+            for (int j = 0; j < kPF; ++j) {
+                const int kb = kb0 + j;
+                if (kb < nkb) {
+                    const int s = kb % C::kStages;
+                    const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
+                    if (kb + kPF - 1 < nkb) load_a_rows(rowp, kb + kPF - 1, vr[(j + kPF - 1) % kPF]);
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (dbg && tid == 0 && kb == 0) {
+                        asm volatile("" ::"f"(vr[0][3][1].w));   // wait for the last load of k-block 0
+                        dbg[9] = clock64();
+                    }
+                    store_a_rows(vr[j], a_hi(s), a_lo(s), r0, chunk);
+                    if (dbg && tid == 0 && kb == 0) dbg[10] = clock64();
+                    fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar(s));
+                    if (dbg && tid == 0 && kb == 0) dbg[11] = clock64();
                 }
             }
+        }
         }
         if (dbg && tid == 0) dbg[1] = clock64();          // all A tiles produced
         // ================= epilogue =================
