@@ -27,7 +27,9 @@ struct RowMap {
 };
 
 __host__ __device__ inline long long rowmap_off(const RowMap& m, int r) {
-    return m.offset + (long long)(r / m.rpc) * m.chunk_stride + (long long)(r % m.rpc) * m.row_stride;
+    if (m.rpc >= (1 << 30)) return m.offset + (long long)r * m.row_stride;      // plain matrix: no division
+    const int q = r / m.rpc;
+    return m.offset + (long long)q * m.chunk_stride + (long long)(r - q * m.rpc) * m.row_stride;
 }
 
 inline RowMap plain_map(long long ld, long long offset = 0) {
