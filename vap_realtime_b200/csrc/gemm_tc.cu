@@ -81,6 +81,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// Multicast variant: the box lands at the same smem offset in every CTA of `mask` and completes tx bytes on
+// the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -238,6 +261,7 @@ template <int BN, bool LN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
     using C = Cfg<BN>;
+    const long long t_entry = g.dbg ? clock64() : 0;
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B tiles need 1024 B alignment
@@ -280,7 +304,10 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     long long* dbg = g.dbg ? g.dbg + 16 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
-    if (dbg && tid == 0) dbg[0] = clock64();
+    if (dbg && tid == 0) {
+        dbg[0] = clock64();
+        dbg[12] = t_entry;
+    }
 
     if (warp < kProducerWarps) {
         // ================= A producers =================
@@ -467,6 +494,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
     tc_fence_before();
     __syncthreads();
     if (warp == kProducerWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
+    if (dbg && tid == kThreads - 32) dbg[13] = clock64();      // after the TMEM free (warp 9)
 }
 
 // ---- K = 256 kernel: A resident in shared memory, loop over N ------------------------------------
@@ -482,11 +510,16 @@ constexpr int kR_EpiBytes = kProducerWarps * 32 * kEpiPitch * 4;
 constexpr int kR_SmemBytes = kR_ABytes + kR_WStages * 2 * kR_WTile + kR_EpiBytes + 1024 + 256;
 constexpr int kR_MaxSub = 8;                                // 8 x 64 = 512 TMEM columns
 
-template <bool LN>
+// CL = 2: thread-block cluster of two CTAs with adjacent M tiles (same N range).  Each CTA fetches HALF of
+// every W tile (32 of its 64 rows, per plane) and TMA-multicasts it into both CTAs, halving the L2 -> SM
+// weight traffic that otherwise dominates these small-K GEMMs (every M tile re-reads all of W).
+template <bool LN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc_k256(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                int ns /* 64-wide subtiles per CTA */, int tmem_cols) {
     pdl_trigger();
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -511,7 +544,7 @@ k_gemm_tc_k256(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, con
         for (int i = 0; i < 4; ++i) mbar_init(a_full(i), kProducerWarps);
         for (int i = 0; i < kR_WStages; ++i) {
             mbar_init(w_full(i), 1);
-            mbar_init(w_empty(i), 1);
+            mbar_init(w_empty(i), CL);           // every CTA of the cluster must have consumed the slot
         }
         for (int i = 0; i < kR_MaxSub; ++i) mbar_init(acc_full(i), 1);
         fence_barrier_init();
@@ -520,7 +553,8 @@ k_gemm_tc_k256(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, con
     }
     if (warp == kProducerWarps + 1) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all();              // peers' barriers are initialised before any multicast / remote arrive
+    else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -623,8 +657,16 @@ k_gemm_tc_k256(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, con
                     const uint32_t ph = (uint32_t)(it / kR_WStages) & 1u;
                     mbar_wait(w_empty(s), ph ^ 1u);
                     mbar_arrive_expect_tx(w_full(s), 2u * kR_WTile);
-                    tma_load_2d(w_hi(s), &map_hi, kb * kBK, n_begin + st * 64, w_full(s));
-                    tma_load_2d(w_lo(s), &map_lo, kb * kBK, n_begin + st * 64, w_full(s));
+                    if (CL > 1) {
+                        // this CTA's share: rows [32*crank, 32*crank + 32) of the 64-row tile, both planes, to all CTAs
+                        const uint32_t off = crank * (kR_WTile / CL);
+                        const int nrow = n_begin + st * 64 + (int)crank * (64 / CL);
+                        tma_load_2d_mc(w_hi(s) + off, &map_hi, kb * kBK, nrow, w_full(s), kMask);
+                        tma_load_2d_mc(w_lo(s) + off, &map_lo, kb * kBK, nrow, w_full(s), kMask);
+                    } else {
+                        tma_load_2d(w_hi(s), &map_hi, kb * kBK, n_begin + st * 64, w_full(s));
+                        tma_load_2d(w_lo(s), &map_lo, kb * kBK, n_begin + st * 64, w_full(s));
+                    }
                 }
             }
         }
@@ -650,14 +692,16 @@ k_gemm_tc_k256(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, con
                         umma_bf16(tm_acc, ah, wl, idesc, 1u);
                         umma_bf16(tm_acc, ah, wh, idesc, 1u);
                     }
-                    umma_commit(w_empty(s));
+                    if (CL > 1) umma_commit_mc(w_empty(s), kMask);     // frees the slot in every CTA that writes into it
+                    else umma_commit(w_empty(s));
                 }
                 umma_commit(acc_full(st));
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all();              // no CTA leaves while a peer may still multicast into it
+    else __syncthreads();
     if (warp == kProducerWarps + 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
@@ -749,6 +793,10 @@ bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vec
         err = "k_split_planes launch failed";
         return false;
     }
+    if (N % 64 == 0) {      // half-tile boxes for the 2-CTA multicast of the K = 256 kernel
+        if (!encode_plane(&out.map_hi32, hi, N, K, 32, err)) return false;
+        if (!encode_plane(&out.map_lo32, lo, N, K, 32, err)) return false;
+    }
     for (int t = 0; t < 3; ++t) {
         out.has_tile[t] = (N % kTileN[t] == 0);
         if (!out.has_tile[t]) continue;
@@ -758,8 +806,10 @@ bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vec
     if (!ensure_attr<64>(&err) || !ensure_attr<128>(&err) || !ensure_attr<256>(&err)) return false;
     static OncePerDevice k256_once;
     if (k256_once.first()) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc_k256<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc_k256<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc_k256<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc_k256<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc_k256<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc_k256<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kR_SmemBytes);
         if (e != cudaSuccess) {
             err = std::string("cudaFuncSetAttribute(k_gemm_tc_k256) failed: ") + cudaGetErrorString(e);
             return false;
@@ -815,7 +865,7 @@ int pick_k256_split(const GemmArgs& g) {
     for (int split = 1; split <= nsub; ++split) {
         if (nsub % split != 0 || nsub / split > kR_MaxSub) continue;
         if (best == 0) best = split;                    // smallest legal split (least A re-conversion)
-        if (mt * split <= 148) best = split;            // ... but use idle SMs while one wave still suffices
+        if ((mt + 1) / 2 * 2 * split <= 148) best = split;   // ... but use idle SMs while one wave still suffices
     }
     return best;
 }
@@ -827,9 +877,17 @@ int launch_gemm_tc(const GemmArgs& g, const TcWeight& w, TcWorkspace& ws, cudaSt
             const int ns = g.N / 64 / split;
             int cols = 32;
             while (cols < ns * 64) cols *= 2;
-            dim3 grid((g.M + kBM - 1) / kBM, split);
-            if (g.ln_w) launch_k(k_gemm_tc_k256<true>, grid, dim3(kThreads), kR_SmemBytes, st, g, w.map_hi[0], w.map_lo[0], ns, cols);
-            else launch_k(k_gemm_tc_k256<false>, grid, dim3(kThreads), kR_SmemBytes, st, g, w.map_hi[0], w.map_lo[0], ns, cols);
+            const int mt = (g.M + kBM - 1) / kBM;
+            if (ws.cluster2 && mt >= 2) {
+                // pairs of M tiles share every W tile through TMA multicast; an odd tile count gets one idle partner
+                dim3 grid((mt + 1) / 2 * 2, split);
+                if (g.ln_w) launch_k_cluster(k_gemm_tc_k256<true, 2>, grid, dim3(kThreads), kR_SmemBytes, st, 2, g, w.map_hi32, w.map_lo32, ns, cols);
+                else launch_k_cluster(k_gemm_tc_k256<false, 2>, grid, dim3(kThreads), kR_SmemBytes, st, 2, g, w.map_hi32, w.map_lo32, ns, cols);
+                return 1;
+            }
+            dim3 grid(mt, split);
+            if (g.ln_w) launch_k(k_gemm_tc_k256<true, 1>, grid, dim3(kThreads), kR_SmemBytes, st, g, w.map_hi[0], w.map_lo[0], ns, cols);
+            else launch_k(k_gemm_tc_k256<false, 1>, grid, dim3(kThreads), kR_SmemBytes, st, g, w.map_hi[0], w.map_lo[0], ns, cols);
             return 1;
         }
     }
@@ -980,8 +1038,8 @@ int tc_selftest(int device, int variant, double* max_rel_err, std::string& repor
             long long st[16];
             cudaMemcpy(st, ddbg, sizeof st, cudaMemcpyDeviceToHost);
             char tb[400];
-            snprintf(tb, sizeof tb, " | %.2f us/launch warm; CTA0 cycles: ptrs %lld, loads_issued %lld, data0 %lld, stored0 %lld, arrived0 %lld, first_full %lld, produced %lld, last_mma_issue %lld, last_tma %lld, accum_ready %lld, epi_done %lld",
-                     ms * 1000.f / 20.f, st[7] - st[0], st[8] - st[0], st[9] - st[0], st[10] - st[0], st[11] - st[0], st[4] - st[0],
+            snprintf(tb, sizeof tb, " | %.2f us/launch warm; CTA0 cycles: prologue %lld, exit %lld, ptrs %lld, loads_issued %lld, data0 %lld, stored0 %lld, arrived0 %lld, first_full %lld, produced %lld, last_mma_issue %lld, last_tma %lld, accum_ready %lld, epi_done %lld",
+                     ms * 1000.f / 20.f, st[0] - st[12], st[13] - st[0], st[7] - st[0], st[8] - st[0], st[9] - st[0], st[10] - st[0], st[11] - st[0], st[4] - st[0],
                      st[1] - st[0], st[5] - st[0], st[6] - st[0], st[2] - st[0], st[3] - st[0]);
             timing_note = tb;
             cudaEventDestroy(e0);

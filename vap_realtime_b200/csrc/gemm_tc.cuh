@@ -30,11 +30,13 @@ struct TcWeight {
     int N = 0, K = 0;
     bool has_tile[3] = {false, false, false};      // N tile widths 64 / 128 / 256
     CUtensorMap map_hi[3], map_lo[3];              // 2D {K, N}, box {64, tile}, SWIZZLE_128B
+    CUtensorMap map_hi32, map_lo32;                // box {64, 32}: half tiles for the 2-CTA multicast
 };
 
 struct TcWorkspace {
     int force_bn = 0;                // 0 = pick the tile width from the grid size, else 64 / 128 / 256
     int use_k256 = 1;                // route K = 256 GEMMs to the resident-A kernel
+    int cluster2 = 1;                // ... as 2-CTA clusters that multicast the W tiles
 };
 
 // Splits W (device fp32 [N][K]) into bf16 planes and encodes the TMA descriptors.

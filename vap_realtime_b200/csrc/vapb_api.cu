@@ -943,7 +943,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -958,6 +958,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "fork") h->opt_fork = value ? 1 : 0;
         else if (k == "splitk") h->opt_splitk = value ? 1 : 0;
         else if (k == "conv4p") h->opt_conv4p = value & 3;
+        else if (k == "cluster2") h->tcws.cluster2 = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -991,6 +992,7 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "fork") *value = h->opt_fork;
     else if (k == "splitk") *value = h->opt_splitk;
     else if (k == "conv4p") *value = h->opt_conv4p;
+    else if (k == "cluster2") *value = h->tcws.cluster2;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
