@@ -9,7 +9,7 @@ from vap_realtime_b200.engine import VapEngine
 B = int(os.environ.get("B", "64")); T = int(os.environ.get("T", "50"))
 w, _ = bench.load_weights("vap")
 audio = torch.from_numpy(bench.make_audio(B, 8)).cuda()
-configs = {"default": {}, "pdl": {"pdl": 1}, "no_k256": {"k256": 0}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "no_cluster2": {"cluster2": 0}, "conv4p_0": {"conv4p": 0}, "conv4p_3": {"conv4p": 3},
+configs = {"default": {}, "pdl": {"pdl": 1}, "no_k256": {"k256": 0}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "conv4p_0": {"conv4p": 0}, "conv4p_3": {"conv4p": 3},
            "ln_unfused": {"fuse_ln": 0}, "lstm_unfused": {"lstm_fused": 0}, "gemm_fp32": {"gemm": 0}}
 for name, opts in configs.items():
     eng = VapEngine(w, 20, T, max_streams=B)

@@ -36,7 +36,7 @@ struct TcWeight {
 struct TcWorkspace {
     int force_bn = 0;                // 0 = pick the tile width from the grid size, else 64 / 128 / 256
     int use_k256 = 1;                // route K = 256 GEMMs to the resident-A kernel
-    int cluster2 = 1;                // ... as 2-CTA clusters that multicast the W tiles
+    int cluster2 = 0;                // ... as 2-CTA clusters that multicast the W tiles (measured 2 % slower at B = 64: r01_l_option_ablation.log)
 };
 
 // Splits W (device fp32 [N][K]) into bf16 planes and encodes the TMA descriptors.
