@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Per-op clock64 deltas of the per-stream persistent transformer kernel (cluster 0 / CTA 0), GPU box only."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from vap_realtime_b200.engine import VapEngine
+
+B = int(os.environ.get("B", "64")); T = int(os.environ.get("T", "50"))
+w, _ = bench.load_weights("vap")
+audio = torch.from_numpy(bench.make_audio(B, 8)).cuda()
+eng = VapEngine(w, 20, T, max_streams=B)
+eng.set_option("gemm", 1)
+DBG_OP = int(os.environ.get("DBG_OP", "8"))
+eng.set_option("fused_dbg", 1 + DBG_OP)
+out = torch.empty((B, 6), device="cuda")
+for i in range(T + 10):
+    eng.step(audio[i % 8], out=out)
+torch.cuda.synchronize()
+clk = eng.tap("fused_clocks")
+names = ["gather_ring"]
+for l in range(3):
+    if l > 0: names.append(f"L{l}.kv_cross")
+    names += [f"L{l}.ln_qkv", f"L{l}.attn", f"L{l}.proj"]
+    if l > 0: names += [f"L{l}.ln_q_cross", f"L{l}.attn_cross", f"L{l}.proj_c"]
+    names += [f"L{l}.ln_ffn1", f"L{l}.ffn2"]
+    if l == 0: names.append("vad")
+names += ["L3.kv_cross", "L3.ln_kv_self", "gather_last"]
+for n, c in zip(names, clk):
+    print(f"{n:16s} {c:9.0f} cyc  {c / 1965.0:7.2f} us")
+fine = clk[len(names):]
+clk = clk[:len(names)]
+labels = ["A loaded(+LN)", "A stored", "first acc_full", "last acc_full", "epilogue done", "barrier passed", "mma: A kb0 ready", "mma: first W ready", "mma: last issue", "tma: first issue", "tma: last issue"]
+print(f"fine stamps of op {DBG_OP} ({names[DBG_OP]}), cycles since op start:")
+for l, v in zip(labels, fine):
+    print(f"   {l:20s} {v:9.0f}")
+print(f"{'total':16s} {clk.sum():9.0f} cyc  {clk.sum() / 1965.0:7.2f} us   (B={B} T={T})")

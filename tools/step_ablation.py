@@ -9,9 +9,12 @@ from vap_realtime_b200.engine import VapEngine
 B = int(os.environ.get("B", "64")); T = int(os.environ.get("T", "50"))
 w, _ = bench.load_weights("vap")
 audio = torch.from_numpy(bench.make_audio(B, 8)).cuda()
-configs = {"default": {}, "pdl": {"pdl": 1}, "no_k256": {"k256": 0}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "conv4p_0": {"conv4p": 0}, "conv4p_3": {"conv4p": 3},
+configs = {"default": {}, "no_fused": {"fused": 0}, "pdl": {"pdl": 1}, "no_k256": {"k256": 0}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "conv4p_0": {"conv4p": 0}, "conv4p_3": {"conv4p": 3},
            "ln_unfused": {"fuse_ln": 0}, "lstm_unfused": {"lstm_fused": 0}, "gemm_fp32": {"gemm": 0}}
+only = [x for x in os.environ.get("ONLY", "").split(",") if x]
 for name, opts in configs.items():
+    if only and name not in only:
+        continue
     eng = VapEngine(w, 20, T, max_streams=B)
     eng.set_option("gemm", 1)
     for k, v in opts.items():

@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvapb200.so")
+LIB_PATH = os.environ.get("VAPB_LIB") or os.path.join(_HERE, "libvapb200.so")   # VAPB_LIB: kernel experiments only
 
 # Every symbol include/vapb200.h declares: (restype, argtypes)
 SIGNATURES = {

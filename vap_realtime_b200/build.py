@@ -7,8 +7,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libvapb200.so")
-SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "vapb_api.cu"]
+LIB = os.environ.get("VAPB_LIB_OUT") or os.path.join(HERE, "libvapb200.so")   # VAPB_LIB_OUT / VAPB_NVCC_EXTRA: kernel experiments
+SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "fused_tf.cu", "vapb_api.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -30,8 +30,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", os.environ.get("VAPB_OBJ_SUFFIX", "") + ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("VAPB_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

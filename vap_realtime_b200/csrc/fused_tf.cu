@@ -1,0 +1,618 @@
+// Per-stream persistent transformer kernel -- see fused_tf.cuh for the scheme.
+//
+// CTA anatomy (320 threads, 1 CTA per SM, cluster of 2 CTAs per stream):
+//   warps 0-7  workers: A producers (fp32 global -> LayerNorm -> smem transpose -> thread-per-row bf16 hi/lo ->
+//              tcgen05.st: the A operand lives in TENSOR MEMORY, so the MMAs read only W from shared memory and
+//              shared memory is left for an 8-deep W ring), GEMM epilogues (tcgen05.ld -> GELU / residual ->
+//              global), attention, gathers, vad
+//   warp 8     TMA producer of the W planes; runs one op AHEAD of the others (weights are constants),
+//              so the ring is already full when the cluster barrier in front of a GEMM opens
+//   warp 9     TMEM owner + the single thread that issues tcgen05.mma
+// All pipelines (W ring, A generations, accumulator slots) carry their phase across ops; the only
+// synchronisation between ops is one cluster barrier (release / acquire, covers global memory).
+// Activations written earlier in the same launch are read with ld.global.cg (L2), never .nc.
+#include "fused_tf.cuh"
+#include "tc_ptx.cuh"
+
+#include <string>
+
+namespace vapb {
+
+namespace {
+
+using namespace tcp;
+
+constexpr int kWorkers = 8;
+constexpr int kThreadsF = (kWorkers + 2) * 32;
+#ifndef VAPB_F_WSTAGES
+#define VAPB_F_WSTAGES 8
+#endif
+constexpr int kWStages = VAPB_F_WSTAGES;
+constexpr int kWTile = 64 * kBK * 2;                  // one plane of a 64 (n) x 64 (k) W tile: 8 KB
+constexpr int kEpiPitch = 36;
+constexpr int kStgPitch = 68;                         // floats per row of the A transpose staging (32 rows x 64 k per quadrant)
+constexpr int kStgFloats = 32 * kStgPitch;
+// union region: A transpose staging (4 quadrants x 2 buffers), epilogue transpose (8 warps), attention K / V / Q / P
+constexpr int kUniBytes = 82 * 1024;
+static_assert(4 * 2 * kStgFloats * 4 <= kUniBytes && kWorkers * 32 * kEpiPitch * 4 <= kUniBytes, "union region too small");
+// TMEM columns: A hi plane [0,128), A lo plane [128,256) (bf16x2 per column, K = 256), accumulators [256,512)
+constexpr uint32_t kTmALo = 128, kTmAcc = 256;
+constexpr int kAccSlots = 4;                          // 4 x 64 accumulator columns
+constexpr int kSmemF = kWStages * 2 * kWTile + kUniBytes + 256 + 1024;
+static_assert(40 + 16 * kWStages + 16 * kAccSlots + 4 <= 256, "barrier block too small");
+constexpr int kKPitch = 68;                           // attention: K rows in smem (float4 reads, conflict free per quarter warp)
+
+__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); }   // the two warps of a TMEM lane quadrant
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// bounded mbarrier wait that names what it was waiting for (a mis-programmed pipeline must fail loudly, never hang)
+__device__ __forceinline__ void fwait(uint32_t bar, uint32_t parity, int tag, int oi) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) {
+            if ((threadIdx.x & 31) == 0)
+                printf("vapb stream kernel: wait %d (1 a_empty 2 acc_full 3 w_empty 4 acc_empty 5 a_full 6 w_full) timed out, op %d block %d warp %d parity %u\n",
+                       tag, oi, blockIdx.x, threadIdx.x >> 5, parity);
+            __trap();
+        }
+    }
+}
+
+struct Ctx {
+    uint32_t wbase, bars, tmem_base;
+    float* uni;            // union region (generic pointer)
+    int tid, warp, lane;
+    int b, r;              // stream index in the batch, CTA rank in the cluster
+    int m0, rows;          // first global row and valid rows of this CTA's M tile
+    int T, t, mode, oi;
+    __device__ __forceinline__ uint32_t w_hi(int s) const { return wbase + (uint32_t)s * 2 * kWTile; }
+    __device__ __forceinline__ uint32_t w_lo(int s) const { return w_hi(s) + kWTile; }
+    __device__ __forceinline__ uint32_t a_full(int kb) const { return bars + 8u * kb; }
+    __device__ __forceinline__ uint32_t a_empty() const { return bars + 32u; }
+    __device__ __forceinline__ uint32_t w_full(int s) const { return bars + 40u + 8u * s; }
+    __device__ __forceinline__ uint32_t w_empty(int s) const { return bars + 40u + 8u * (kWStages + s); }
+    __device__ __forceinline__ uint32_t acc_full(int i) const { return bars + 40u + 16u * kWStages + 8u * i; }
+    __device__ __forceinline__ uint32_t acc_empty(int i) const { return bars + 40u + 16u * kWStages + 8u * (kAccSlots + i); }
+    __device__ __forceinline__ uint32_t tmem_slot() const { return bars + 40u + 16u * kWStages + 16u * kAccSlots; }
+};
+
+// One 32 x 32 block of the accumulator: TMEM -> registers -> per-warp smem transpose -> (GELU, + R) -> global.
+template <bool HAS_R, bool GELU>
+__device__ __forceinline__ void epi_block(const uint32_t (&raw)[32], float* tbuf, int lane, int rows_valid, const float* Rb,
+                                          float* Cb, int ld, int ncol) {
+    const int sub = lane >> 3;
+    const int c4 = (lane & 7) * 4;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(tbuf + lane * kEpiPitch + 4 * q) =
+            make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                        __uint_as_float(raw[4 * q + 3]));
+    __syncwarp();
+    float4 res[8];
+    if (HAS_R) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = 4 * it + sub;
+            res[it] = (rr < rows_valid) ? ldcg4(Rb + (size_t)rr * ld + ncol + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int rr = 4 * it + sub;
+        float4 x = *reinterpret_cast<const float4*>(tbuf + rr * kEpiPitch + c4);
+        if (GELU) {
+            x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+        }
+        if (HAS_R) {
+            x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
+        }
+        if (rr < rows_valid) *reinterpret_cast<float4*>(Cb + (size_t)rr * ld + ncol + c4) = x;
+    }
+    __syncwarp();
+}
+
+// ---- GEMM, worker side: write the A operand of every 256-wide K chunk to tensor memory, then drain the accumulators ----
+// Load layout: warp (q = warp & 3, hf = warp >> 2) holds rows 32q + 16hf + [0,16) of the tile, all 256 columns
+// (8 lanes per row, 128-bit coalesced loads; LayerNorm statistics by 8-lane shuffles).  tcgen05.st wants one thread
+// per row (TMEM lane = row, reachable only from warps with warp % 4 == q), so every 64-wide k-block is transposed
+// through a [32 rows][64] staging tile shared by the two warps of the quadrant: thread l then owns row 32q + l,
+// columns 32hf + [0,32) of the k-block, splits them into bf16 hi / lo pairs and stores 16 + 16 packed columns.
+template <bool LN>
+__device__ __forceinline__ void gemm_workers(const Ctx& c, const FOp& op, int n_begin, int ns, int gst, int ga, long long* d2) {
+    const int kch = op.K >> 8;
+    const int q = c.warp & 3, hf = c.warp >> 2, lg = c.lane >> 3, chunk = c.lane & 7;
+    float* stg = c.uni + q * (2 * kStgFloats);
+    const uint32_t tm_q = c.tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int kc = 0; kc < kch; ++kc) {
+        float4 vr[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = 32 * q + 16 * hf + 4 * i + lg;
+            if (r < c.rows) {
+                const float* p = op.A + (size_t)(c.m0 + r) * op.lda + kc * 256 + chunk * 8;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    vr[j][i][0] = ldcg4(p + j * kBK);
+                    vr[j][i][1] = ldcg4(p + j * kBK + 4);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    vr[j][i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vr[j][i][1] = vr[j][i][0];
+                }
+            }
+        }
+        if constexpr (LN) {
+            float mean[4], rstd[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    sum += (vr[j][i][0].x + vr[j][i][0].y) + (vr[j][i][0].z + vr[j][i][0].w) + (vr[j][i][1].x + vr[j][i][1].y) +
+                           (vr[j][i][1].z + vr[j][i][1].w);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                mean[i] = sum * (1.0f / 256.0f);
+                float sq = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d[8] = {vr[j][i][0].x - mean[i], vr[j][i][0].y - mean[i], vr[j][i][0].z - mean[i],
+                                        vr[j][i][0].w - mean[i], vr[j][i][1].x - mean[i], vr[j][i][1].y - mean[i],
+                                        vr[j][i][1].z - mean[i], vr[j][i][1].w - mean[i]};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) sq = fmaf(d[e], d[e], sq);
+                }
+                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                rstd[i] = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-5f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(op.ln_w + j * kBK + chunk * 8));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(op.ln_w + j * kBK + chunk * 8 + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(op.ln_b + j * kBK + chunk * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(op.ln_b + j * kBK + chunk * 8 + 4));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4& a = vr[j][i][0];
+                    float4& b = vr[j][i][1];
+                    a.x = (a.x - mean[i]) * rstd[i] * w0.x + b0.x; a.y = (a.y - mean[i]) * rstd[i] * w0.y + b0.y;
+                    a.z = (a.z - mean[i]) * rstd[i] * w0.z + b0.z; a.w = (a.w - mean[i]) * rstd[i] * w0.w + b0.w;
+                    b.x = (b.x - mean[i]) * rstd[i] * w1.x + b1.x; b.y = (b.y - mean[i]) * rstd[i] * w1.y + b1.y;
+                    b.z = (b.z - mean[i]) * rstd[i] * w1.z + b1.z; b.w = (b.w - mean[i]) * rstd[i] * w1.w + b1.w;
+                }
+            }
+        }
+        if (d2 && kc == 0) {
+            asm volatile("" ::"f"(vr[3][3][1].w));
+            d2[1] = clock64();                 // A loads landed (+ LayerNorm done)
+        }
+        // the MMAs of the previous A generation must have finished reading the A columns of tensor memory
+        fwait(c.a_empty(), (uint32_t)((ga + kc) & 1) ^ 1u, 1, c.oi);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float* sb = stg + (j & 1) * kStgFloats;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float* dst = sb + (16 * hf + 4 * i + lg) * kStgPitch + chunk * 8;
+                *reinterpret_cast<float4*>(dst) = vr[j][i][0];
+                *reinterpret_cast<float4*>(dst + 4) = vr[j][i][1];
+            }
+            pair_sync(q);
+            const float* src = sb + c.lane * kStgPitch + 32 * hf;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float4 f = *reinterpret_cast<const float4*>(src + 4 * e);
+                split2(f.x, f.y, hi[2 * e], lo[2 * e]);
+                split2(f.z, f.w, hi[2 * e + 1], lo[2 * e + 1]);
+            }
+            tmem_st16(tm_q + (uint32_t)(j * 32 + 16 * hf), hi);
+            tmem_st16(tm_q + kTmALo + (uint32_t)(j * 32 + 16 * hf), lo);
+            tmem_st_wait();
+            tc_fence_before();
+            if (c.lane == 0) mbar_arrive(c.a_full(j));
+        }
+    }
+    if (d2) d2[2] = clock64();                 // A planes stored
+    // ---- epilogue: one 32 x 32 block per warp and 64-wide subtile
+    const int quad = q, half = hf;
+    const int rows_valid = min(32, c.rows - quad * 32);
+    float* tbuf = c.uni + c.warp * (32 * kEpiPitch);     // aliases the A staging: every warp is past it once an accumulator is complete
+    const uint32_t tm_row = c.tmem_base + ((uint32_t)(quad * 32) << 16);
+    const size_t rowoff = (size_t)(c.m0 + quad * 32) * op.ldc;
+    float* Cb = op.C + rowoff;
+    const float* Rb = op.R ? op.R + rowoff : nullptr;
+    for (int st = 0; st < ns; ++st) {
+        const int g = gst + st, slot = g & (kAccSlots - 1);
+        fwait(c.acc_full(slot), (uint32_t)(g / kAccSlots) & 1u, 2, c.oi);
+        tc_fence_after();
+        if (d2 && st == 0) d2[3] = clock64();          // first accumulator complete
+        if (d2 && st == ns - 1) d2[4] = clock64();     // last accumulator complete
+        uint32_t raw[32];
+        tmem_ld32(tm_row + kTmAcc + (uint32_t)(slot * 64 + half * 32), raw);
+        tc_fence_before();
+        if (c.lane == 0) mbar_arrive(c.acc_empty(slot));     // slot may be overwritten by a later subtile / op
+        const int ncol = n_begin + st * 64 + half * 32;
+        if (Rb) {
+            if (op.act == 1) epi_block<true, true>(raw, tbuf, c.lane, rows_valid, Rb, Cb, op.ldc, ncol);
+            else epi_block<true, false>(raw, tbuf, c.lane, rows_valid, Rb, Cb, op.ldc, ncol);
+        } else {
+            if (op.act == 1) epi_block<false, true>(raw, tbuf, c.lane, rows_valid, Rb, Cb, op.ldc, ncol);
+            else epi_block<false, false>(raw, tbuf, c.lane, rows_valid, Rb, Cb, op.ldc, ncol);
+        }
+    }
+    if (d2) d2[5] = clock64();                 // epilogue of warp 0 done
+}
+
+// ---- causal ALiBi attention (modules.py:82-110, 170-212) for the (sequence, head) units of this CTA ----
+// fp32 FMA; a warp works on two adjacent query rows at a time so every K / V read from smem feeds two rows.
+__device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op) {
+    float* sm = c.uni;                                     // union region (idle between GEMMs)
+    const int T = c.T, t = c.t;
+    float* sK = sm;                                        // [T + 4][68]  (rows up to t4 - 1 are written)
+    float* sV = sK + (T + 4) * kKPitch;                    // [T + 4][64]
+    float* sQ = sV + (T + 4) * 64;                         // [8 warps][2][64]
+    float* sP = sQ + kWorkers * 128;                       // [8 warps][2][128]
+    const int warp = c.warp, lane = c.lane;
+    float* q0s = sQ + warp * 128;
+    float* q1s = q0s + 64;
+    float* p0s = sP + warp * 256;
+    float* p1s = p0s + 128;
+    const int t4 = (t + 3) & ~3;
+    for (int u = 0; u < 4; ++u) {
+        int n, h;
+        if (c.mode == 0) { n = 2 * c.b + (u >> 1); h = 2 * c.r + (u & 1); }
+        else { n = 2 * c.b + c.r; h = u; }
+        const int kvn = op.sibling ? (n ^ 1) : n;
+        for (int i = c.tid; i < t4 * 16; i += kWorkers * 32) {
+            const int j = i >> 4, q = (i & 15) * 4;
+            float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+            if (j < t) {
+                const size_t rr = (size_t)kvn * T + j;
+                kk = ldcg4(op.Kp + rr * op.ldk + h * 64 + q);
+                vv = ldcg4(op.V + rr * op.ldv + h * 64 + q);
+            }
+            *reinterpret_cast<float4*>(sK + j * kKPitch + q) = kk;
+            *reinterpret_cast<float4*>(sV + j * 64 + q) = vv;
+        }
+        workers_sync();
+        const float slope = __ldg(op.slopes + h);
+        for (int i0 = 2 * warp; i0 < T; i0 += 2 * kWorkers) {
+            const int i1 = i0 + 1;
+            float* o0p = op.O + ((size_t)n * T + i0) * op.ldo + h * 64;
+            float* o1p = o0p + op.ldo;
+            if (i0 >= t) {                      // rows beyond the valid window: defined zeros
+                *reinterpret_cast<float2*>(o0p + 2 * lane) = make_float2(0.f, 0.f);
+                if (i1 < T) *reinterpret_cast<float2*>(o1p + 2 * lane) = make_float2(0.f, 0.f);
+                continue;
+            }
+            const bool v1 = i1 < t;
+            {
+                const float* qr = op.Q + ((size_t)n * T + i0) * op.ldq + h * 64;
+                const float2 a = __ldcg(reinterpret_cast<const float2*>(qr) + lane);
+                float2 b = make_float2(0.f, 0.f);
+                if (v1) b = __ldcg(reinterpret_cast<const float2*>(qr + op.ldq) + lane);
+                *reinterpret_cast<float2*>(q0s + 2 * lane) = a;
+                *reinterpret_cast<float2*>(q1s + 2 * lane) = b;
+            }
+            __syncwarp();
+            const int imax = v1 ? i1 : i0;
+            const int nj = (imax >> 5) + 1;     // 32-key blocks that hold visible keys
+            float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int d4 = 0; d4 < 16; ++d4) {
+                const float4 qa = *reinterpret_cast<const float4*>(q0s + 4 * d4);
+                const float4 qb = *reinterpret_cast<const float4*>(q1s + 4 * d4);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    if (jj < nj) {
+                        const int j = min(lane + 32 * jj, t4 - 1);
+                        const float4 k4 = *reinterpret_cast<const float4*>(sK + j * kKPitch + 4 * d4);
+                        s0[jj] = fmaf(qa.x, k4.x, s0[jj]); s0[jj] = fmaf(qa.y, k4.y, s0[jj]);
+                        s0[jj] = fmaf(qa.z, k4.z, s0[jj]); s0[jj] = fmaf(qa.w, k4.w, s0[jj]);
+                        s1[jj] = fmaf(qb.x, k4.x, s1[jj]); s1[jj] = fmaf(qb.y, k4.y, s1[jj]);
+                        s1[jj] = fmaf(qb.z, k4.z, s1[jj]); s1[jj] = fmaf(qb.w, k4.w, s1[jj]);
+                    }
+                }
+            }
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = lane + 32 * jj;
+                const float bias = slope * (float)j;
+                s0[jj] = (jj < nj && j <= i0) ? s0[jj] * 0.0625f + bias : -INFINITY;
+                s1[jj] = (jj < nj && j <= i1 && v1) ? s1[jj] * 0.0625f + bias : -INFINITY;
+                m0 = fmaxf(m0, s0[jj]);
+                m1 = fmaxf(m1, s1[jj]);
+            }
+            m0 = warp_max_f(m0);
+            m1 = warp_max_f(m1);
+            if (!v1) m1 = 0.f;
+            float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = lane + 32 * jj;
+                s0[jj] = (jj < nj && j <= i0) ? expf(s0[jj] - m0) : 0.f;
+                s1[jj] = (jj < nj && j <= i1 && v1) ? expf(s1[jj] - m1) : 0.f;
+                sum0 += s0[jj];
+                sum1 += s1[jj];
+            }
+            sum0 = warp_sum_f(sum0);
+            sum1 = warp_sum_f(sum1);
+            const float inv0 = 1.0f / sum0, inv1 = v1 ? 1.0f / sum1 : 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                if (jj < nj) {
+                    p0s[lane + 32 * jj] = s0[jj] * inv0;
+                    p1s[lane + 32 * jj] = s1[jj] * inv1;
+                }
+            }
+            __syncwarp();
+            float2 oa = make_float2(0.f, 0.f), ob = oa;
+            for (int j = 0; j <= imax; j += 4) {       // rows up to t4 - 1 are zero filled, p is 0 beyond the row's own limit
+                const float4 pa = *reinterpret_cast<const float4*>(p0s + j);
+                const float4 pb = *reinterpret_cast<const float4*>(p1s + j);
+                const float2 va = *reinterpret_cast<const float2*>(sV + (j + 0) * 64 + 2 * lane);
+                const float2 vb = *reinterpret_cast<const float2*>(sV + (j + 1) * 64 + 2 * lane);
+                const float2 vc = *reinterpret_cast<const float2*>(sV + (j + 2) * 64 + 2 * lane);
+                const float2 vd = *reinterpret_cast<const float2*>(sV + (j + 3) * 64 + 2 * lane);
+                oa.x = fmaf(pa.x, va.x, oa.x); oa.y = fmaf(pa.x, va.y, oa.y);
+                ob.x = fmaf(pb.x, va.x, ob.x); ob.y = fmaf(pb.x, va.y, ob.y);
+                oa.x = fmaf(pa.y, vb.x, oa.x); oa.y = fmaf(pa.y, vb.y, oa.y);
+                ob.x = fmaf(pb.y, vb.x, ob.x); ob.y = fmaf(pb.y, vb.y, ob.y);
+                oa.x = fmaf(pa.z, vc.x, oa.x); oa.y = fmaf(pa.z, vc.y, oa.y);
+                ob.x = fmaf(pb.z, vc.x, ob.x); ob.y = fmaf(pb.z, vc.y, ob.y);
+                oa.x = fmaf(pa.w, vd.x, oa.x); oa.y = fmaf(pa.w, vd.y, oa.y);
+                ob.x = fmaf(pb.w, vd.x, ob.x); ob.y = fmaf(pb.w, vd.y, ob.y);
+            }
+            *reinterpret_cast<float2*>(o0p + 2 * lane) = oa;
+            if (i1 < T) *reinterpret_cast<float2*>(o1p + 2 * lane) = v1 ? ob : make_float2(0.f, 0.f);
+            __syncwarp();
+        }
+        workers_sync();
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    Ctx c;
+    c.wbase = (smem_u32(smem_raw) + 1023u) & ~1023u;       // W ring first: SWIZZLE_128B tiles need 1024 B alignment
+    c.uni = reinterpret_cast<float*>(smem_raw + (c.wbase - smem_u32(smem_raw)) + kWStages * 2 * kWTile);
+    c.bars = c.wbase + kWStages * 2 * kWTile + kUniBytes;
+    c.tid = threadIdx.x;
+    c.warp = c.tid >> 5;
+    c.lane = c.tid & 31;
+    c.r = (int)cluster_ctarank();
+    c.b = blockIdx.x >> 1;
+    c.T = p.T;
+    c.mode = p.mode;
+    if (p.mode == 0) { c.m0 = c.b * 2 * p.T; c.rows = 2 * p.T; }
+    else { c.m0 = (2 * c.b + c.r) * p.T; c.rows = p.T; }
+    const int id = __ldg(p.ids + c.b);
+    const int cnt = __ldg(p.count + id) + 1;           // frames including the one appended this step
+    c.t = cnt < p.T ? cnt : p.T;
+
+    if (c.warp == kWorkers && c.lane == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(c.a_full(i), kWorkers);
+        mbar_init(c.a_empty(), 1);
+        for (int i = 0; i < kWStages; ++i) {
+            mbar_init(c.w_full(i), 1);
+            mbar_init(c.w_empty(i), 1);
+        }
+        for (int i = 0; i < kAccSlots; ++i) {
+            mbar_init(c.acc_full(i), 1);
+            mbar_init(c.acc_empty(i), kWorkers);
+        }
+        fence_barrier_init();
+    }
+    if (c.warp == kWorkers + 1) tmem_alloc(c.tmem_slot(), 512u);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c.tmem_base) : "r"(c.tmem_slot()));
+
+    int gst = 0, ga = 0, wi = 0;     // running counters: accumulator subtiles, A generations, W stages
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && c.tid == 0;
+
+    for (int oi = 0; oi < p.n_ops; ++oi) {
+        const FOp& op = p.ops[oi];
+        c.oi = oi;
+        const int kind = __shfl_sync(0xffffffffu, op.kind, 0);
+        if (dbg) p.dbg[oi] = clock64();
+        // fine stamps of one op (p.dbg_op) of cluster 0 / CTA 0: slots 40.. of the clock buffer
+        long long* d2 = (p.dbg != nullptr && blockIdx.x == 0 && oi == p.dbg_op) ? p.dbg + 40 : nullptr;
+        if (d2 && c.tid == 0) d2[0] = clock64();
+        int n_begin = 0, ns = 0, kch = 0;
+        if (kind == FOP_GEMM) {
+            kch = op.K >> 8;
+            if (c.mode == 0) { ns = op.N >> 7; n_begin = c.r * (op.N >> 1); }
+            else { ns = op.N >> 6; n_begin = 0; }
+        }
+        // loaded from global memory: tell the compiler they are warp-uniform (loop bounds of the MMA / TMA warps)
+        ns = __shfl_sync(0xffffffffu, ns, 0);
+        kch = __shfl_sync(0xffffffffu, kch, 0);
+        n_begin = __shfl_sync(0xffffffffu, n_begin, 0);
+        if (c.warp < kWorkers) {
+            // =========================== workers ===========================
+            if (kind == FOP_GEMM) {
+                if (op.ln_w) gemm_workers<true>(c, op, n_begin, ns, gst, ga, c.tid == 0 ? d2 : nullptr);
+                else gemm_workers<false>(c, op, n_begin, ns, gst, ga, c.tid == 0 ? d2 : nullptr);
+            } else if (kind == FOP_ATTN) {
+                attention_workers(c, op);
+            } else if (kind == FOP_GATHER_RING) {
+                // X rows of channel r = ring rows oldest first, zero rows above t (vap_main.py:274-283)
+                const int ch = c.r;
+                const float* rg = p.ring + ((size_t)id * 2 + ch) * p.T * kD;
+                float* xo = p.X + (size_t)(2 * c.b + ch) * p.T * kD;
+                for (int i = c.tid; i < p.T * 64; i += kWorkers * 32) {
+                    const int j = i >> 6, q = i & 63;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < c.t) {
+                        const int slot = (cnt - c.t + j) % p.T;
+                        v = ldcg4(rg + (size_t)slot * kD + 4 * q);
+                    }
+                    *reinterpret_cast<float4*>(xo + (size_t)j * kD + 4 * q) = v;
+                }
+                if (c.r == 0 && c.tid == 0) p.tvalid[c.b] = c.t;
+            } else if (kind == FOP_VAD) {
+                // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
+                if (c.warp == 0) {
+                    const float* xr = p.X + ((size_t)(2 * c.b + c.r) * p.T + (c.t - 1)) * kD + 8 * c.lane;
+                    const float4 x0 = ldcg4(xr), x1 = ldcg4(xr + 4);
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane));
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane + 4));
+                    float s = 0.f;
+                    s = fmaf(x0.x, w0.x, s); s = fmaf(x0.y, w0.y, s); s = fmaf(x0.z, w0.z, s); s = fmaf(x0.w, w0.w, s);
+                    s = fmaf(x1.x, w1.x, s); s = fmaf(x1.y, w1.y, s); s = fmaf(x1.z, w1.z, s); s = fmaf(x1.w, w1.w, s);
+                    s = warp_sum_f(s) + __ldg(p.va_b);
+                    if (c.lane == 0) p.out[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
+                }
+            } else if (kind == FOP_GATHER_LAST) {
+                if (c.warp == 0) {
+                    const int n = 2 * c.b + c.r;
+                    const float* xr = p.X + ((size_t)n * p.T + (c.t - 1)) * kD + 8 * c.lane;
+                    float* xo = p.Xl + (size_t)n * kD + 8 * c.lane;
+                    *reinterpret_cast<float4*>(xo) = ldcg4(xr);
+                    *reinterpret_cast<float4*>(xo + 4) = ldcg4(xr + 4);
+                }
+            }
+            cl_arrive();
+            cl_wait();
+            if (d2 && c.tid == 0) d2[6] = clock64();   // cluster barrier passed
+        } else if (c.warp == kWorkers) {
+            // =========================== TMA producer (one op ahead) ===========================
+            if (kind == FOP_GEMM && elect_one()) {
+                int w = wi;
+                if (d2) d2[10] = clock64();            // TMA: first issue of this op
+                // tile order = MMA order: subtiles go in PAIRS that are issued interleaved (see the MMA warp)
+                for (int kc = 0; kc < kch; ++kc)
+                    for (int sp = 0; sp < ns; sp += 2)
+                        for (int kb = 0; kb < 4; ++kb)
+                            for (int sub = 0; sub < 2; ++sub, ++w) {
+                                const int s = w % kWStages;
+                                const uint32_t ph = (uint32_t)(w / kWStages) & 1u;
+                                fwait(c.w_empty(s), ph ^ 1u, 3, c.oi);
+                                mbar_arrive_expect_tx(c.w_full(s), 2u * kWTile);
+                                tma_load_2d(c.w_hi(s), &op.map_hi, kc * 256 + kb * kBK, n_begin + (sp + sub) * 64, c.w_full(s));
+                                tma_load_2d(c.w_lo(s), &op.map_lo, kc * 256 + kb * kBK, n_begin + (sp + sub) * 64, c.w_full(s));
+                            }
+                if (d2) d2[11] = clock64();            // TMA: last issue
+            }
+            __syncwarp();
+            if (oi > 0) cl_wait();
+            cl_arrive();
+        } else {
+            // =========================== MMA issuer ===========================
+            if (kind == FOP_GEMM && elect_one()) {
+                const uint32_t lead = 1u;
+                const uint32_t tmb = c.tmem_base;
+                constexpr uint32_t idesc = make_idesc(64);
+                int w = wi;
+                // An accumulator takes one dependent MMA per ~90 cycles whatever its width, a 128 x 64 x 16 MMA is
+                // 32 cycles of tensor work: two subtiles (two accumulators) are issued interleaved so that the pipe
+                // is not idle between dependent MMAs (measured: 94 -> ~45 cycles per MMA).
+                for (int kc = 0; kc < kch; ++kc) {
+                    for (int sp = 0; sp < ns; sp += 2) {
+                        const int g0 = gst + sp, g1 = g0 + 1;
+                        const int slot0 = g0 & (kAccSlots - 1), slot1 = g1 & (kAccSlots - 1);
+                        if (kc == 0) {
+                            fwait(c.acc_empty(slot0), ((uint32_t)(g0 / kAccSlots) & 1u) ^ 1u, 4, c.oi);
+                            fwait(c.acc_empty(slot1), ((uint32_t)(g1 / kAccSlots) & 1u) ^ 1u, 4, c.oi);
+                            tc_fence_after();
+                        }
+                        const uint32_t tm_acc0 = tmb + kTmAcc + (uint32_t)(slot0 * 64);
+                        const uint32_t tm_acc1 = tmb + kTmAcc + (uint32_t)(slot1 * 64);
+                        for (int kb = 0; kb < 4; ++kb, w += 2) {
+                            const int s0 = w % kWStages, s1 = (w + 1) % kWStages;
+                            const uint32_t ph0 = (uint32_t)(w / kWStages) & 1u, ph1 = (uint32_t)((w + 1) / kWStages) & 1u;
+                            if (sp == 0) fwait(c.a_full(kb), (uint32_t)(ga + kc) & 1u, 5, c.oi);
+                            if (d2 && lead && kc == 0 && sp == 0 && kb == 0) d2[7] = clock64();      // MMA: A k-block 0 ready
+                            fwait(c.w_full(s0), ph0, 6, c.oi);
+                            fwait(c.w_full(s1), ph1, 6, c.oi);
+                            tc_fence_after();
+                            if (d2 && lead && kc == 0 && sp == 0 && kb == 0) d2[8] = clock64();      // MMA: first W stages ready
+#pragma unroll
+                            for (int k = 0; k < kBK / kUmmaK; ++k) {
+                                const uint32_t koff = (uint32_t)k * kUmmaK * 2;
+                                const uint32_t ah = tmb + (uint32_t)(kb * 32 + k * 8), al = ah + kTmALo;
+                                const uint64_t wh0 = make_desc(c.w_hi(s0) + koff), wl0 = make_desc(c.w_lo(s0) + koff);
+                                const uint64_t wh1 = make_desc(c.w_hi(s1) + koff), wl1 = make_desc(c.w_lo(s1) + koff);
+                                const uint32_t first = (kc | kb | k) ? 1u : 0u;
+                                umma_bf16_ta_p(tm_acc0, al, wh0, idesc, first, lead);      // small terms first
+                                umma_bf16_ta_p(tm_acc1, al, wh1, idesc, first, lead);
+                                umma_bf16_ta_p(tm_acc0, ah, wl0, idesc, 1u, lead);
+                                umma_bf16_ta_p(tm_acc1, ah, wl1, idesc, 1u, lead);
+                                umma_bf16_ta_p(tm_acc0, ah, wh0, idesc, 1u, lead);
+                                umma_bf16_ta_p(tm_acc1, ah, wh1, idesc, 1u, lead);
+                            }
+                            umma_commit_p(c.w_empty(s0), lead);
+                            umma_commit_p(c.w_empty(s1), lead);
+                        }
+                        if (kc == kch - 1) {
+                            umma_commit_p(c.acc_full(slot0), lead);
+                            umma_commit_p(c.acc_full(slot1), lead);
+                        }
+                    }
+                    umma_commit_p(c.a_empty(), lead);
+                }
+                if (d2 && lead) d2[9] = clock64();             // MMA: last issue
+            }
+            __syncwarp();
+            cl_arrive();
+            cl_wait();
+        }
+        if (kind == FOP_GEMM) {
+            gst += ns;
+            ga += kch;
+            wi += ns * 4 * kch;
+        }
+    }
+    if (c.warp == kWorkers) cl_wait();          // the TMA warp is one barrier behind
+    if (dbg) p.dbg[p.n_ops] = clock64();
+    tc_fence_before();
+    __syncthreads();
+    if (c.warp == kWorkers + 1) tmem_dealloc(c.tmem_base, 512u);
+}
+
+}  // namespace
+
+size_t fused_smem_bytes() { return kSmemF; }
+
+bool fused_prepare(std::string& err) {
+    static OncePerDevice once;
+    if (!once.first()) return true;
+    cudaError_t e = cudaFuncSetAttribute(k_stream_tf, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemF);
+    if (e != cudaSuccess) {
+        err = std::string("cudaFuncSetAttribute(k_stream_tf) failed: ") + cudaGetErrorString(e);
+        return false;
+    }
+    return true;
+}
+
+cudaError_t launch_fused_tf(const FusedParams& p, int B, cudaStream_t st) {
+    return launch_k_cluster(k_stream_tf, dim3(2 * B), dim3(kThreadsF), kSmemF, st, 2, p);
+}
+
+}  // namespace vapb

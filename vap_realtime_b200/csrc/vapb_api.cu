@@ -3,6 +3,7 @@
 #include "../../include/vapb200.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "fused_tf.cuh"
 
 #include <cuda_runtime.h>
 
@@ -110,6 +111,11 @@ struct vapb_ctx {
     float* audio_stage = nullptr;    // device staging for vapb_step_host
     float* out_stage = nullptr;
     TcWorkspace tcws;                // bf16 hi/lo activation planes for the tcgen05 path
+    // per-stream persistent transformer kernel (fused_tf.cu): op list in device memory
+    FOp* fops = nullptr;
+    int n_fops = 0;
+    long long* fused_clk = nullptr;  // optional clock64 stamps per op (option fused_dbg)
+    int opt_fused = 1, opt_fused_dbg = 0;
 
     // taps
     std::map<std::string, std::pair<float*, size_t>> taps;
@@ -410,7 +416,7 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
 
 // Final cross layer with the query side restricted to the newest frame of every sequence (exact:
 // nothing downstream reads the other positions, vap_main.py:316-317).  K/V still cover the window.
-void transformer_layer_last(Step& s, const LayerWeights& lw) {
+void transformer_layer_last(Step& s, const LayerWeights& lw, bool kv_done = false) {
     vapb_ctx* c = s.c;
     const int NL = 2 * s.B, R = NL * c->T;
     const RowMap pd = plain_map(kD), pf = plain_map(kFF), p2 = plain_map(2 * kD);
@@ -432,9 +438,11 @@ void transformer_layer_last(Step& s, const LayerWeights& lw) {
         mark(s, sibling ? "attn_cross_last" : "attn_self_last");
     };
     // keys / values over the whole window: cross attention from the RAW sibling input, self attention from LN(X)
-    gemm(s, "gemm_kv_cross", c->X, pd, lw.Wkv_c, &lw.tc_kv_c, nullptr, nullptr, pd, c->KVc, p2, R, 2 * kD, kD, 0);
-    ln_gemm("gemm_ln_kv_self", c->X, c->Z, R, lw.ln_sa_w, lw.ln_sa_b, lw.sa.Wqkv + (size_t)kD * kD, &lw.sa.tc_kv, c->QKV, p2, 2 * kD, 0);
-    launch_gather_last(c->X, c->tvalid, c->Xl, NL, c->T, s.st); mark(s, "gather_last");
+    if (!kv_done) {
+        gemm(s, "gemm_kv_cross", c->X, pd, lw.Wkv_c, &lw.tc_kv_c, nullptr, nullptr, pd, c->KVc, p2, R, 2 * kD, kD, 0);
+        ln_gemm("gemm_ln_kv_self", c->X, c->Z, R, lw.ln_sa_w, lw.ln_sa_b, lw.sa.Wqkv + (size_t)kD * kD, &lw.sa.tc_kv, c->QKV, p2, 2 * kD, 0);
+        launch_gather_last(c->X, c->tvalid, c->Xl, NL, c->T, s.st); mark(s, "gather_last");
+    }
     // self attention of the newest frame
     ln_gemm("gemm_ln_q_last", c->Xl, c->Zl, NL, lw.ln_sa_w, lw.ln_sa_b, lw.sa.Wqkv, &lw.sa.tc_q, c->Ql, pd, kD, 0);
     attn_last(c->Ql, c->QKV, c->QKV + kD, 2 * kD, lw.sa.slopes, 0);
@@ -446,6 +454,83 @@ void transformer_layer_last(Step& s, const LayerWeights& lw) {
     // feed forward
     ln_gemm("gemm_ln_ffn1_last", c->Xl, c->Zl, NL, lw.ln_ff_w, lw.ln_ff_b, lw.W1, &lw.tc_w1, c->Hl, pf, kFF, 1);
     gemm(s, "gemm_ffn2_last", c->Hl, pf, lw.W2, &lw.tc_w2, nullptr, c->Xl, pd, c->Xl, pd, NL, kD, kFF, 0);
+}
+
+// ---- op list of the per-stream persistent transformer kernel (fused_tf.cu) ---------------
+FOp fop_gemm(const float* A, int lda, int K, const TcWeight& w, const float* ln_w, const float* ln_b, const float* R, float* C,
+             int ldc, int N, int act) {
+    FOp o;
+    memset(&o, 0, sizeof o);
+    o.kind = FOP_GEMM;
+    o.map_hi = w.map_hi[0];
+    o.map_lo = w.map_lo[0];
+    o.A = A; o.lda = lda; o.K = K; o.ln_w = ln_w; o.ln_b = ln_b; o.R = R; o.C = C; o.ldc = ldc; o.N = N; o.act = act;
+    return o;
+}
+FOp fop_attn(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O, const float* slopes, int sibling) {
+    FOp o;
+    memset(&o, 0, sizeof o);
+    o.kind = FOP_ATTN;
+    o.Q = Q; o.ldq = ldq; o.Kp = K; o.ldk = ldk; o.V = V; o.ldv = ldv; o.O = O; o.ldo = kD; o.slopes = slopes; o.sibling = sibling;
+    return o;
+}
+FOp fop_misc(int kind) {
+    FOp o;
+    memset(&o, 0, sizeof o);
+    o.kind = kind;
+    return o;
+}
+
+int build_fused_ops(vapb_ctx* c) {
+    std::vector<FOp> ops;
+    ops.push_back(fop_misc(FOP_GATHER_RING));
+    for (int l = 0; l < 3; ++l) {
+        const LayerWeights& lw = c->layers[l];
+        if (lw.cross) ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_kv_c, nullptr, nullptr, nullptr, c->KVc, 2 * kD, 2 * kD, 0));
+        ops.push_back(fop_gemm(c->X, kD, kD, lw.sa.tc_qkv, lw.ln_sa_w, lw.ln_sa_b, nullptr, c->QKV, 3 * kD, 3 * kD, 0));
+        ops.push_back(fop_attn(c->QKV, 3 * kD, c->QKV + kD, 3 * kD, c->QKV + 2 * kD, 3 * kD, c->O, lw.sa.slopes, 0));
+        ops.push_back(fop_gemm(c->O, kD, kD, lw.sa.tc_proj, nullptr, nullptr, c->X, c->X, kD, kD, 0));
+        if (lw.cross) {
+            ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_q_c, lw.ln_src_w, lw.ln_src_b, nullptr, c->Qc, kD, kD, 0));
+            ops.push_back(fop_attn(c->Qc, kD, c->KVc, 2 * kD, c->KVc + kD, 2 * kD, c->O, lw.slopes_c, 1));
+            ops.push_back(fop_gemm(c->O, kD, kD, lw.tc_proj_c, nullptr, nullptr, c->X, c->X, kD, kD, 0));
+        }
+        ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_w1, lw.ln_ff_w, lw.ln_ff_b, nullptr, c->Hd, kFF, kFF, 1));
+        ops.push_back(fop_gemm(c->Hd, kFF, kFF, lw.tc_w2, nullptr, nullptr, c->X, c->X, kD, kD, 0));
+        if (l == 0 && c->head_kind == VAPB_HEAD_VAP) ops.push_back(fop_misc(FOP_VAD));
+    }
+    {   // pruned last layer: only its window-wide K / V projections and the newest-frame gather
+        const LayerWeights& lw = c->layers[3];
+        ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_kv_c, nullptr, nullptr, nullptr, c->KVc, 2 * kD, 2 * kD, 0));
+        ops.push_back(fop_gemm(c->X, kD, kD, lw.sa.tc_kv, lw.ln_sa_w, lw.ln_sa_b, nullptr, c->QKV, 2 * kD, 2 * kD, 0));
+        ops.push_back(fop_misc(FOP_GATHER_LAST));
+    }
+    c->n_fops = (int)ops.size();
+    void* d = nullptr;
+    if (cudaMalloc(&d, ops.size() * sizeof(FOp)) != cudaSuccess) return fail(c, VAPB_ENOMEM, "cudaMalloc(fused op list) failed");
+    c->allocs.push_back(d);
+    if (cudaMemcpy(d, ops.data(), ops.size() * sizeof(FOp), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(c, VAPB_ECUDA, "cudaMemcpy(fused op list) failed");
+    c->fops = static_cast<FOp*>(d);
+    if (cudaMalloc(&d, 64 * sizeof(long long)) != cudaSuccess) return fail(c, VAPB_ENOMEM, "cudaMalloc(fused clocks) failed");
+    c->allocs.push_back(d);
+    cudaMemset(d, 0, 64 * sizeof(long long));
+    c->fused_clk = static_cast<long long*>(d);
+    std::string err;
+    if (!fused_prepare(err)) return fail(c, VAPB_ECUDA, "%s", err.c_str());
+    return 0;
+}
+
+void fused_transformer(Step& s) {
+    vapb_ctx* c = s.c;
+    FusedParams p;
+    p.ops = c->fops; p.n_ops = c->n_fops; p.T = c->T; p.mode = (2 * c->T <= 128) ? 0 : 1;
+    p.ring = c->ring; p.count = c->count; p.ids = c->ids_dev; p.tvalid = c->tvalid; p.X = c->X; p.Xl = c->Xl;
+    p.va_w = c->va_w; p.va_b = c->va_b; p.out = s.out;
+    p.dbg = c->opt_fused_dbg ? c->fused_clk : nullptr;
+    p.dbg_op = c->opt_fused_dbg - 1;          // fused_dbg = 1 + index of the op that gets fine stamps
+    launch_fused_tf(p, s.B, s.st);
+    mark(s, "fused_tf");
 }
 
 void enqueue_step(Step& s) {
@@ -524,6 +609,13 @@ void enqueue_step(Step& s) {
         }
         mark(s, "ln_gelu_ring");
     }
+    const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
+    if (c->opt_gemm == 1 && c->opt_fused && prune && c->fops) {
+        // ---- ring gather, ar_channel, vad, cross layers 0-1 and the K/V of the pruned last layer: ONE launch,
+        //      a cluster of two CTAs per stream (fused_tf.cu); then the newest-frame tail of the last layer
+        fused_transformer(s);
+        transformer_layer_last(s, c->layers[3], true);
+    } else {
     // ---- window of the last T embeddings, oldest first (vap_main.py:274-283)
     launch_gather_ring(c->ring, c->count, c->ids_dev, c->X, c->tvalid, B, T, st); mark(s, "gather_ring");
     const size_t RX = (size_t)NC * T * kD;
@@ -535,11 +627,11 @@ void enqueue_step(Step& s) {
         launch_vad(c->X, c->tvalid, c->va_w, c->va_b, s.out, B, T, st); mark(s, "vad");
     }
     // ---- ar: three TransformerStereoLayers (modules.py:289-300, 395-423)
-    const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
     for (int li = 0; li < 3; ++li) {
         if (li == 2 && prune) transformer_layer_last(s, c->layers[3]);
         else transformer_layer(s, c->layers[1 + li]);
         tap_copy(s, c->tap_cross[li], c->X, RX);
+    }
     }
     // ---- combinator + projection head + aggregation; advances the frame counters
     HeadArgs h;
@@ -753,6 +845,8 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         if (!ok) FAIL_CREATE(VAPB_ECUDA, "tcgen05 setup failed: %s", terr.c_str());
     }
 
+    if (build_fused_ops(c) != 0) FAIL_CREATE(VAPB_ECUDA, "%s", c->err.c_str());
+
     // taps (allocated lazily when keep_taps is switched on)
     if (cudaDeviceSynchronize() != cudaSuccess) FAIL_CREATE(VAPB_ECUDA, "device error during create: %s", cudaGetErrorString(cudaGetLastError()));
     *out = c;
@@ -943,7 +1037,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -959,6 +1053,8 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "splitk") h->opt_splitk = value ? 1 : 0;
         else if (k == "conv4p") h->opt_conv4p = value & 3;
         else if (k == "cluster2") h->tcws.cluster2 = value ? 1 : 0;
+        else if (k == "fused") h->opt_fused = value ? 1 : 0;
+        else if (k == "fused_dbg") h->opt_fused_dbg = value;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -993,6 +1089,8 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "splitk") *value = h->opt_splitk;
     else if (k == "conv4p") *value = h->opt_conv4p;
     else if (k == "cluster2") *value = h->tcws.cluster2;
+    else if (k == "fused") *value = h->opt_fused;
+    else if (k == "fused_dbg") *value = h->opt_fused_dbg;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
@@ -1019,6 +1117,14 @@ int vapb_debug_tensor(vapb_handle h, const char* name, float* host_out, size_t c
         for (int c = 0; c < NC; ++c)
             memcpy(tmp.data() + (size_t)c * h->L[i] * kD, raw.data() + ((size_t)c * rows + h->halo[i]) * kD,
                    (size_t)h->L[i] * kD * sizeof(float));
+        n = tmp.size();
+    } else if (k == "fused_clocks") {
+        // clock64 deltas (cycles) per op of the stream kernel, cluster 0 / CTA 0 (option fused_dbg)
+        std::vector<long long> clk(64);
+        CK(h, cudaMemcpy(clk.data(), h->fused_clk, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+        tmp.resize((size_t)h->n_fops);
+        for (int i = 0; i < h->n_fops; ++i) tmp[i] = (float)(clk[i + 1] - clk[i]);
+        for (int i = 1; i < 12; ++i) tmp.push_back(clk[40 + i] ? (float)(clk[40 + i] - clk[40]) : 0.f);   // fine stamps of op fused_dbg - 1
         n = tmp.size();
     } else if (k == "lstm_out") { src = h->Y; n = (size_t)NC * h->n_lstm * kD; }
     else if (k == "e") { src = h->ebuf; n = (size_t)NC * kD; }
