@@ -25,7 +25,7 @@ using namespace tcp;
 constexpr int kWorkers = 8;
 constexpr int kThreadsF = (kWorkers + 2) * 32;
 #ifndef VAPB_F_WSTAGES
-#define VAPB_F_WSTAGES 8
+#define VAPB_F_WSTAGES 6
 #endif
 constexpr int kWStages = VAPB_F_WSTAGES;
 constexpr int kWTile = 64 * kBK * 2;                  // one plane of a 64 (n) x 64 (k) W tile: 8 KB
@@ -33,13 +33,13 @@ constexpr int kEpiPitch = 36;
 constexpr int kStgPitch = 68;                         // floats per row of the A transpose staging (32 rows x 64 k per quadrant)
 constexpr int kStgFloats = 32 * kStgPitch;
 // union region: A transpose staging (4 quadrants x 2 buffers), epilogue transpose (8 warps), attention K / V / Q / P
-constexpr int kUniBytes = 82 * 1024;
-static_assert(4 * 2 * kStgFloats * 4 <= kUniBytes && kWorkers * 32 * kEpiPitch * 4 <= kUniBytes, "union region too small");
+constexpr int kUniBytes = 128 * 1024;              // = two heads x (K hi/lo + V hi/lo) x 16 KB for the tensor-core attention
+static_assert(8 * 128 * 128 == kUniBytes && 4 * 32 * kStgPitch * 4 <= 4 * 128 * 128 && 4 * 2 * kStgFloats * 4 <= kUniBytes && kWorkers * 32 * kEpiPitch * 4 <= kUniBytes, "union region too small");
 // TMEM columns: A hi plane [0,128), A lo plane [128,256) (bf16x2 per column, K = 256), accumulators [256,512)
 constexpr uint32_t kTmALo = 128, kTmAcc = 256;
 constexpr int kAccSlots = 4;                          // 4 x 64 accumulator columns
 constexpr int kSmemF = kWStages * 2 * kWTile + kUniBytes + 256 + 1024;
-static_assert(40 + 16 * kWStages + 16 * kAccSlots + 4 <= 256, "barrier block too small");
+static_assert(40 + 16 * kWStages + 16 * kAccSlots + 8 + 48 <= 256, "barrier block too small");
 constexpr int kKPitch = 68;                           // attention: K rows in smem (float4 reads, conflict free per quarter warp)
 
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
@@ -67,7 +67,7 @@ __device__ __forceinline__ void fwait(uint32_t bar, uint32_t parity, int tag, in
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 2000000000LL) {
             if ((threadIdx.x & 31) == 0)
-                printf("vapb stream kernel: wait %d (1 a_empty 2 acc_full 3 w_empty 4 acc_empty 5 a_full 6 w_full) timed out, op %d block %d warp %d parity %u\n",
+                printf("vapb stream kernel: wait %d (1 a_empty 2 acc_full 3 w_empty 4 acc_empty 5 a_full 6 w_full 7 s_full 8 o_full 9 att_in 10 p_ready) timed out, op %d block %d warp %d parity %u\n",
                        tag, oi, blockIdx.x, threadIdx.x >> 5, parity);
             __trap();
         }
@@ -90,6 +90,12 @@ struct Ctx {
     __device__ __forceinline__ uint32_t acc_full(int i) const { return bars + 40u + 16u * kWStages + 8u * i; }
     __device__ __forceinline__ uint32_t acc_empty(int i) const { return bars + 40u + 16u * kWStages + 8u * (kAccSlots + i); }
     __device__ __forceinline__ uint32_t tmem_slot() const { return bars + 40u + 16u * kWStages + 16u * kAccSlots; }
+    // tensor-core attention: inputs staged / S complete / P written (per head) / O complete (per head)
+    __device__ __forceinline__ uint32_t att_in() const { return tmem_slot() + 8u; }
+    __device__ __forceinline__ uint32_t s_full() const { return tmem_slot() + 16u; }
+    __device__ __forceinline__ uint32_t p_ready(int x) const { return tmem_slot() + 24u + 8u * x; }
+    __device__ __forceinline__ uint32_t o_full(int x) const { return tmem_slot() + 40u + 8u * x; }
+    __device__ __forceinline__ uint32_t uni_u32() const { return wbase + kWStages * 2 * kWTile; }
 };
 
 // One 32 x 32 block of the accumulator: TMEM -> registers -> per-warp smem transpose -> (GELU, + R) -> global.
@@ -125,6 +131,29 @@ __device__ __forceinline__ void epi_block(const uint32_t (&raw)[32], float* tbuf
         if (rr < rows_valid) *reinterpret_cast<float4*>(Cb + (size_t)rr * ld + ncol + c4) = x;
     }
     __syncwarp();
+}
+
+// One 64-wide k-block of a 128-row operand tile: coalesced-layout registers (warp (q, hf) holds rows 32q + 16hf + 4i + lg,
+// 8 floats at column 8 * chunk) -> staging tile of the quadrant -> thread-per-row bf16 hi / lo -> 16 + 16 TMEM columns.
+__device__ __forceinline__ void stage_to_tmem(const Ctx& c, const float4 (&v)[4][2], float* sb, uint32_t tm_hi, uint32_t tm_lo) {
+    const int q = c.warp & 3, hf = c.warp >> 2, lg = c.lane >> 3, chunk = c.lane & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float* dst = sb + (16 * hf + 4 * i + lg) * kStgPitch + chunk * 8;
+        *reinterpret_cast<float4*>(dst) = v[i][0];
+        *reinterpret_cast<float4*>(dst + 4) = v[i][1];
+    }
+    pair_sync(q);
+    const float* src = sb + c.lane * kStgPitch + 32 * hf;
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float4 f = *reinterpret_cast<const float4*>(src + 4 * e);
+        split2(f.x, f.y, hi[2 * e], lo[2 * e]);
+        split2(f.z, f.w, hi[2 * e + 1], lo[2 * e + 1]);
+    }
+    tmem_st16(tm_hi + (uint32_t)(16 * hf), hi);
+    tmem_st16(tm_lo + (uint32_t)(16 * hf), lo);
 }
 
 // ---- GEMM, worker side: write the A operand of every 256-wide K chunk to tensor memory, then drain the accumulators ----
@@ -212,24 +241,7 @@ __device__ __forceinline__ void gemm_workers(const Ctx& c, const FOp& op, int n_
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float* sb = stg + (j & 1) * kStgFloats;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float* dst = sb + (16 * hf + 4 * i + lg) * kStgPitch + chunk * 8;
-                *reinterpret_cast<float4*>(dst) = vr[j][i][0];
-                *reinterpret_cast<float4*>(dst + 4) = vr[j][i][1];
-            }
-            pair_sync(q);
-            const float* src = sb + c.lane * kStgPitch + 32 * hf;
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float4 f = *reinterpret_cast<const float4*>(src + 4 * e);
-                split2(f.x, f.y, hi[2 * e], lo[2 * e]);
-                split2(f.z, f.w, hi[2 * e + 1], lo[2 * e + 1]);
-            }
-            tmem_st16(tm_q + (uint32_t)(j * 32 + 16 * hf), hi);
-            tmem_st16(tm_q + kTmALo + (uint32_t)(j * 32 + 16 * hf), lo);
+            stage_to_tmem(c, vr[j], stg + (j & 1) * kStgFloats, tm_q + (uint32_t)(j * 32), tm_q + kTmALo + (uint32_t)(j * 32));
             tmem_st_wait();
             tc_fence_before();
             if (c.lane == 0) mbar_arrive(c.a_full(j));
@@ -266,132 +278,224 @@ __device__ __forceinline__ void gemm_workers(const Ctx& c, const FOp& op, int n_
     if (d2) d2[5] = clock64();                 // epilogue of warp 0 done
 }
 
-// ---- causal ALiBi attention (modules.py:82-110, 170-212) for the (sequence, head) units of this CTA ----
-// fp32 FMA; a warp works on two adjacent query rows at a time so every K / V read from smem feeds two rows.
-__device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op) {
-    float* sm = c.uni;                                     // union region (idle between GEMMs)
-    const int T = c.T, t = c.t;
-    float* sK = sm;                                        // [T + 4][68]  (rows up to t4 - 1 are written)
-    float* sV = sK + (T + 4) * kKPitch;                    // [T + 4][64]
-    float* sQ = sV + (T + 4) * 64;                         // [8 warps][2][64]
-    float* sP = sQ + kWorkers * 128;                       // [8 warps][2][128]
-    const int warp = c.warp, lane = c.lane;
-    float* q0s = sQ + warp * 128;
-    float* q1s = q0s + 64;
-    float* p0s = sP + warp * 256;
-    float* p1s = p0s + 128;
-    const int t4 = (t + 3) & ~3;
-    for (int u = 0; u < 4; ++u) {
-        int n, h;
-        if (c.mode == 0) { n = 2 * c.b + (u >> 1); h = 2 * c.r + (u & 1); }
-        else { n = 2 * c.b + c.r; h = u; }
-        const int kvn = op.sibling ? (n ^ 1) : n;
-        for (int i = c.tid; i < t4 * 16; i += kWorkers * 32) {
-            const int j = i >> 4, q = (i & 15) * 4;
-            float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
-            if (j < t) {
-                const size_t rr = (size_t)kvn * T + j;
-                kk = ldcg4(op.Kp + rr * op.ldk + h * 64 + q);
-                vv = ldcg4(op.V + rr * op.ldv + h * 64 + q);
-            }
-            *reinterpret_cast<float4*>(sK + j * kKPitch + q) = kk;
-            *reinterpret_cast<float4*>(sV + j * 64 + q) = vv;
-        }
-        workers_sync();
-        const float slope = __ldg(op.slopes + h);
-        for (int i0 = 2 * warp; i0 < T; i0 += 2 * kWorkers) {
-            const int i1 = i0 + 1;
-            float* o0p = op.O + ((size_t)n * T + i0) * op.ldo + h * 64;
-            float* o1p = o0p + op.ldo;
-            if (i0 >= t) {                      // rows beyond the valid window: defined zeros
-                *reinterpret_cast<float2*>(o0p + 2 * lane) = make_float2(0.f, 0.f);
-                if (i1 < T) *reinterpret_cast<float2*>(o1p + 2 * lane) = make_float2(0.f, 0.f);
-                continue;
-            }
-            const bool v1 = i1 < t;
-            {
-                const float* qr = op.Q + ((size_t)n * T + i0) * op.ldq + h * 64;
-                const float2 a = __ldcg(reinterpret_cast<const float2*>(qr) + lane);
-                float2 b = make_float2(0.f, 0.f);
-                if (v1) b = __ldcg(reinterpret_cast<const float2*>(qr + op.ldq) + lane);
-                *reinterpret_cast<float2*>(q0s + 2 * lane) = a;
-                *reinterpret_cast<float2*>(q1s + 2 * lane) = b;
-            }
-            __syncwarp();
-            const int imax = v1 ? i1 : i0;
-            const int nj = (imax >> 5) + 1;     // 32-key blocks that hold visible keys
-            float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-            for (int d4 = 0; d4 < 16; ++d4) {
-                const float4 qa = *reinterpret_cast<const float4*>(q0s + 4 * d4);
-                const float4 qb = *reinterpret_cast<const float4*>(q1s + 4 * d4);
+// ---- causal ALiBi attention (modules.py:82-110, 170-212) on the tensor cores, two heads per round ----
+//   S = Q K^T (bf16 x3, A = Q in tensor memory, B = K in smem)  ->  thread-per-row masked softmax with the ALiBi
+//   bias, P written over S as bf16 hi / lo  ->  O = P V (A = P in tensor memory, B = V in smem, MN-major: V stays
+//   [key][dim], no transpose)  ->  O rows to global.
+// Tile rows: mode 0 puts sequence 0 in rows 0..63 and sequence 1 in rows 64..127 (T <= 64 valid each), so a TMEM lane
+// quadrant never mixes sequences and S is block diagonal (the off-diagonal blocks of P are written as zeros);
+// mode 1 has one sequence per CTA (rows 0..T-1).  K / V tile rows use the same mapping (sibling channel when
+// cross-attending).  TMEM columns: Q_x hi/lo at 64x (+32), S_x / P_x at 128 + 128x, O_x at 384 + 64x.
+// P of the 32-key chunk c lives in the 32 columns of S chunk c (16 hi + 16 lo), so overwriting S in place is safe.
+constexpr uint32_t kTmQ = 0, kTmS = 128, kTmO = 384;
+constexpr int kAttPlane = 128 * 128;                  // bytes of one bf16 plane of a [128 keys][64 dims] tile
+__host__ __device__ constexpr uint32_t make_idesc_bmn(int bn) { return make_idesc(bn) | (1u << 16); }   // B operand MN-major
+
+struct AttMap {            // tile row -> (sequence, position)
+    int mode, b, r, T;
+    __device__ __forceinline__ int seq(int rr) const { return mode == 0 ? 2 * b + (rr >> 6) : 2 * b + r; }
+    __device__ __forceinline__ int pos(int rr) const { return mode == 0 ? (rr & 63) : rr; }
+};
+
+__device__ __forceinline__ void att_load_rows(const Ctx& c, const AttMap& am, const float* base, int ld, int h, int sib, int limit,
+                                              float4 (&v)[4][2]) {
+    const int q = c.warp & 3, hf = c.warp >> 2, lg = c.lane >> 3, chunk = c.lane & 7;
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    if (jj < nj) {
-                        const int j = min(lane + 32 * jj, t4 - 1);
-                        const float4 k4 = *reinterpret_cast<const float4*>(sK + j * kKPitch + 4 * d4);
-                        s0[jj] = fmaf(qa.x, k4.x, s0[jj]); s0[jj] = fmaf(qa.y, k4.y, s0[jj]);
-                        s0[jj] = fmaf(qa.z, k4.z, s0[jj]); s0[jj] = fmaf(qa.w, k4.w, s0[jj]);
-                        s1[jj] = fmaf(qb.x, k4.x, s1[jj]); s1[jj] = fmaf(qb.y, k4.y, s1[jj]);
-                        s1[jj] = fmaf(qb.z, k4.z, s1[jj]); s1[jj] = fmaf(qb.w, k4.w, s1[jj]);
+    for (int i = 0; i < 4; ++i) {
+        const int rr = 32 * q + 16 * hf + 4 * i + lg;
+        const int pos = am.pos(rr);
+        if (pos < limit) {
+            const float* p = base + ((size_t)(am.seq(rr) ^ sib) * am.T + pos) * ld + h * 64 + chunk * 8;
+            v[i][0] = ldcg4(p);
+            v[i][1] = ldcg4(p + 4);
+        } else {
+            v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i][1] = v[i][0];
+        }
+    }
+}
+// rows of a [128][64] operand tile -> bf16 hi / lo planes in the SWIZZLE_128B layout (row = 128 bytes)
+__device__ __forceinline__ void att_store_planes(const Ctx& c, const float4 (&v)[4][2], uint32_t hi_plane, uint32_t lo_plane) {
+    const int q = c.warp & 3, hf = c.warp >> 2, lg = c.lane >> 3, chunk = c.lane & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = 32 * q + 16 * hf + 4 * i + lg;
+        uint32_t h[4], l[4];
+        split2(v[i][0].x, v[i][0].y, h[0], l[0]);
+        split2(v[i][0].z, v[i][0].w, h[1], l[1]);
+        split2(v[i][1].x, v[i][1].y, h[2], l[2]);
+        split2(v[i][1].z, v[i][1].w, h[3], l[3]);
+        const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(chunk ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_plane + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_plane + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3])
+                     : "memory");
+    }
+}
+
+__device__ __forceinline__ int att_rounds(const Ctx& c) { return c.mode == 0 ? 1 : 2; }
+
+__device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op, int na) {
+    const AttMap am{c.mode, c.b, c.r, c.T};
+    const int q = c.warp & 3, x = c.warp >> 2;             // softmax / epilogue: quadrant q of head x
+    const uint32_t tm_q = c.tmem_base + ((uint32_t)(q * 32) << 16);
+    // smem: K_x hi / lo at x * 2 planes, V_x hi / lo at (4 + 2x) planes; the Q staging tiles (one per quadrant) alias V
+    float* stg = c.uni + kAttPlane + q * kStgFloats;       // float offset kAttPlane = byte offset 4 planes
+    const uint32_t ub = c.uni_u32();
+    for (int round = 0; round < att_rounds(c); ++round) {
+        const uint32_t par = (uint32_t)(na + round) & 1u;
+        const int hbase = c.mode == 0 ? 2 * c.r : 2 * round;
+        // ---- stage Q (tensor memory), K and V (shared memory) of both heads
+        {
+            float4 v[2][4][2];
+#pragma unroll
+            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.Q, op.ldq, hbase + hx, 0, c.t, v[hx]);
+#pragma unroll
+            for (int hx = 0; hx < 2; ++hx) {
+                if (hx) pair_sync(q);          // the partner warp has read head 0 out of the staging tile
+                stage_to_tmem(c, v[hx], stg, tm_q + kTmQ + 64u * hx, tm_q + kTmQ + 64u * hx + 32u);
+            }
+#pragma unroll
+            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.Kp, op.ldk, hbase + hx, op.sibling, c.t, v[hx]);
+#pragma unroll
+            for (int hx = 0; hx < 2; ++hx) att_store_planes(c, v[hx], ub + hx * 2 * kAttPlane, ub + hx * 2 * kAttPlane + kAttPlane);
+            workers_sync();                    // every warp is past the Q staging tiles, which alias the V planes
+#pragma unroll
+            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.V, op.ldv, hbase + hx, op.sibling, c.t, v[hx]);
+#pragma unroll
+            for (int hx = 0; hx < 2; ++hx)
+                att_store_planes(c, v[hx], ub + (4 + 2 * hx) * kAttPlane, ub + (5 + 2 * hx) * kAttPlane);
+            fence_proxy_async();
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(c.att_in());
+        }
+        // ---- softmax of head x, rows of quadrant q: thread = row
+        {
+            const int rr = 32 * q + c.lane;
+            const int i = am.pos(rr);
+            const bool rowv = i < c.t;
+            const int blk = c.mode == 0 ? (q >> 1) : 0;            // 64-key block that holds this row's sequence
+            const int cfirst = 2 * blk;                            // first 32-key chunk of the sequence
+            const int nch = (c.mode == 0 ? (q & 1) : q) + 1;       // chunks with visible keys (causal)
+            const float slope = __ldg(op.slopes + hbase + x);
+            const uint32_t tS = tm_q + kTmS + 128u * x;
+            fwait(c.s_full(), par, 7, c.oi);
+            tc_fence_after();
+            float m = -INFINITY, l = 0.f;
+            for (int cc = 0; cc < nch; ++cc) {
+                uint32_t raw[32];
+                tmem_ld32(tS + 32u * (cfirst + cc), raw);
+                float cm = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int j = 32 * cc + e;
+                    const float sv = (rowv && j <= i) ? __uint_as_float(raw[e]) * 0.0625f + slope * (float)j : -INFINITY;
+                    raw[e] = __float_as_uint(sv);
+                    cm = fmaxf(cm, sv);
+                }
+                const float mn = fmaxf(m, cm);
+                float acc = 0.f;
+                if (mn > -INFINITY) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc += expf(__uint_as_float(raw[e]) - mn);
+                    l = l * expf(m - mn) + acc;
+                }
+                m = mn;
+            }
+            const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+            const float mm = (m > -INFINITY) ? m : 0.f;
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t hi[16], lo[16];
+                const int lc = cc - cfirst;               // chunk index inside the row's own sequence
+                if (lc >= 0 && lc < nch) {
+                    uint32_t raw[32];
+                    tmem_ld32(tS + 32u * cc, raw);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int j0 = 32 * lc + 2 * e, j1 = j0 + 1;
+                        const float p0 = (rowv && j0 <= i) ? expf(__uint_as_float(raw[2 * e]) * 0.0625f + slope * (float)j0 - mm) * inv : 0.f;
+                        const float p1 = (rowv && j1 <= i) ? expf(__uint_as_float(raw[2 * e + 1]) * 0.0625f + slope * (float)j1 - mm) * inv : 0.f;
+                        split2(p0, p1, hi[e], lo[e]);
                     }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { hi[e] = 0u; lo[e] = 0u; }
                 }
+                tmem_st16(tS + 32u * cc, hi);
+                tmem_st16(tS + 32u * cc + 16u, lo);
             }
-            float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = lane + 32 * jj;
-                const float bias = slope * (float)j;
-                s0[jj] = (jj < nj && j <= i0) ? s0[jj] * 0.0625f + bias : -INFINITY;
-                s1[jj] = (jj < nj && j <= i1 && v1) ? s1[jj] * 0.0625f + bias : -INFINITY;
-                m0 = fmaxf(m0, s0[jj]);
-                m1 = fmaxf(m1, s1[jj]);
-            }
-            m0 = warp_max_f(m0);
-            m1 = warp_max_f(m1);
-            if (!v1) m1 = 0.f;
-            float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = lane + 32 * jj;
-                s0[jj] = (jj < nj && j <= i0) ? expf(s0[jj] - m0) : 0.f;
-                s1[jj] = (jj < nj && j <= i1 && v1) ? expf(s1[jj] - m1) : 0.f;
-                sum0 += s0[jj];
-                sum1 += s1[jj];
-            }
-            sum0 = warp_sum_f(sum0);
-            sum1 = warp_sum_f(sum1);
-            const float inv0 = 1.0f / sum0, inv1 = v1 ? 1.0f / sum1 : 0.f;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                if (jj < nj) {
-                    p0s[lane + 32 * jj] = s0[jj] * inv0;
-                    p1s[lane + 32 * jj] = s1[jj] * inv1;
-                }
-            }
+            tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
-            float2 oa = make_float2(0.f, 0.f), ob = oa;
-            for (int j = 0; j <= imax; j += 4) {       // rows up to t4 - 1 are zero filled, p is 0 beyond the row's own limit
-                const float4 pa = *reinterpret_cast<const float4*>(p0s + j);
-                const float4 pb = *reinterpret_cast<const float4*>(p1s + j);
-                const float2 va = *reinterpret_cast<const float2*>(sV + (j + 0) * 64 + 2 * lane);
-                const float2 vb = *reinterpret_cast<const float2*>(sV + (j + 1) * 64 + 2 * lane);
-                const float2 vc = *reinterpret_cast<const float2*>(sV + (j + 2) * 64 + 2 * lane);
-                const float2 vd = *reinterpret_cast<const float2*>(sV + (j + 3) * 64 + 2 * lane);
-                oa.x = fmaf(pa.x, va.x, oa.x); oa.y = fmaf(pa.x, va.y, oa.y);
-                ob.x = fmaf(pb.x, va.x, ob.x); ob.y = fmaf(pb.x, va.y, ob.y);
-                oa.x = fmaf(pa.y, vb.x, oa.x); oa.y = fmaf(pa.y, vb.y, oa.y);
-                ob.x = fmaf(pb.y, vb.x, ob.x); ob.y = fmaf(pb.y, vb.y, ob.y);
-                oa.x = fmaf(pa.z, vc.x, oa.x); oa.y = fmaf(pa.z, vc.y, oa.y);
-                ob.x = fmaf(pb.z, vc.x, ob.x); ob.y = fmaf(pb.z, vc.y, ob.y);
-                oa.x = fmaf(pa.w, vd.x, oa.x); oa.y = fmaf(pa.w, vd.y, oa.y);
-                ob.x = fmaf(pb.w, vd.x, ob.x); ob.y = fmaf(pb.w, vd.y, ob.y);
-            }
-            *reinterpret_cast<float2*>(o0p + 2 * lane) = oa;
-            if (i1 < T) *reinterpret_cast<float2*>(o1p + 2 * lane) = v1 ? ob : make_float2(0.f, 0.f);
-            __syncwarp();
+            if (c.lane == 0) mbar_arrive(c.p_ready(x));
         }
-        workers_sync();
+        // ---- O of head x, rows of quadrant q -> global
+        {
+            fwait(c.o_full(x), par, 8, c.oi);
+            tc_fence_after();
+            const int seq = c.mode == 0 ? 2 * c.b + (q >> 1) : 2 * c.b + c.r;
+            const int i0 = c.mode == 0 ? 32 * (q & 1) : 32 * q;
+            const int rows_valid = min(32, c.T - i0);
+            float* tbuf = c.uni + c.warp * (32 * kEpiPitch);      // aliases K of head 0 (both S products are complete)
+            float* Cb = op.O + ((size_t)seq * c.T + i0) * op.ldo;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t raw[32];
+                tmem_ld32(tm_q + kTmO + 64u * x + 32u * half, raw);
+                epi_block<false, false>(raw, tbuf, c.lane, rows_valid, nullptr, Cb, op.ldo, (hbase + x) * 64 + 32 * half);
+            }
+        }
+        if (round + 1 < att_rounds(c)) {
+            tc_fence_before();
+            workers_sync();                    // K / V / staging tiles and the TMEM columns are reused by the next round
+        }
+    }
+}
+
+// MMA side of the attention (one elected thread)
+__device__ __forceinline__ void attention_mma(const Ctx& c, int na) {
+    const uint32_t ub = c.uni_u32();
+    constexpr uint32_t idesc_s = make_idesc(128);
+    constexpr uint32_t idesc_o = make_idesc_bmn(64);
+    const int nk = c.mode == 0 ? 8 : (c.T + 15) / 16;      // 16-key steps of P V
+    for (int round = 0; round < att_rounds(c); ++round) {
+        const uint32_t par = (uint32_t)(na + round) & 1u;
+        fwait(c.att_in(), par, 9, c.oi);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t koff = (uint32_t)k * kUmmaK * 2;
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                for (int hx = 0; hx < 2; ++hx) {
+                    const uint32_t qh = c.tmem_base + kTmQ + 64u * hx + 8u * k, ql = qh + 32u;
+                    const uint32_t kh = ub + hx * 2 * kAttPlane + koff, kl = kh + kAttPlane;
+                    const uint32_t acc = c.tmem_base + kTmS + 128u * hx;
+                    if (prod == 0) umma_bf16_ta(acc, ql, make_desc(kh), idesc_s, k ? 1u : 0u);
+                    else if (prod == 1) umma_bf16_ta(acc, qh, make_desc(kl), idesc_s, 1u);
+                    else umma_bf16_ta(acc, qh, make_desc(kh), idesc_s, 1u);
+                }
+            }
+        }
+        umma_commit(c.s_full());
+        for (int hx = 0; hx < 2; ++hx) {
+            fwait(c.p_ready(hx), par, 10, c.oi);
+            tc_fence_after();
+            const uint32_t acc = c.tmem_base + kTmO + 64u * hx;
+            const uint32_t vh = ub + (4 + 2 * hx) * kAttPlane, vl = vh + kAttPlane;
+            for (int kk = 0; kk < nk; ++kk) {
+                // keys [16 kk, +16): chunk kk / 2, half kk % 2 -> 8 packed columns of the hi and of the lo half of the chunk
+                const uint32_t ph = c.tmem_base + kTmS + 128u * hx + 32u * (kk >> 1) + 8u * (kk & 1), pl = ph + 16u;
+                const uint32_t voff = (uint32_t)kk * 2048u;        // 16 key rows of 128 bytes
+                umma_bf16_ta(acc, pl, make_desc(vh + voff), idesc_o, kk ? 1u : 0u);
+                umma_bf16_ta(acc, ph, make_desc(vl + voff), idesc_o, 1u);
+                umma_bf16_ta(acc, ph, make_desc(vh + voff), idesc_o, 1u);
+            }
+            umma_commit(c.o_full(hx));
+        }
     }
 }
 
@@ -425,6 +529,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
             mbar_init(c.acc_full(i), 1);
             mbar_init(c.acc_empty(i), kWorkers);
         }
+        mbar_init(c.att_in(), kWorkers);
+        mbar_init(c.s_full(), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(c.p_ready(i), 4);
+            mbar_init(c.o_full(i), 1);
+        }
         fence_barrier_init();
     }
     if (c.warp == kWorkers + 1) tmem_alloc(c.tmem_slot(), 512u);
@@ -433,7 +543,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
     tc_fence_after();
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c.tmem_base) : "r"(c.tmem_slot()));
 
-    int gst = 0, ga = 0, wi = 0;     // running counters: accumulator subtiles, A generations, W stages
+    int gst = 0, ga = 0, wi = 0, na = 0;     // running counters: accumulator subtiles, A generations, W stages, attention rounds
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && c.tid == 0;
 
     for (int oi = 0; oi < p.n_ops; ++oi) {
@@ -460,7 +570,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
                 if (op.ln_w) gemm_workers<true>(c, op, n_begin, ns, gst, ga, c.tid == 0 ? d2 : nullptr);
                 else gemm_workers<false>(c, op, n_begin, ns, gst, ga, c.tid == 0 ? d2 : nullptr);
             } else if (kind == FOP_ATTN) {
-                attention_workers(c, op);
+                attention_workers(c, op, na);
             } else if (kind == FOP_GATHER_RING) {
                 // X rows of channel r = ring rows oldest first, zero rows above t (vap_main.py:274-283)
                 const int ch = c.r;
@@ -579,10 +689,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
                 }
                 if (d2 && lead) d2[9] = clock64();             // MMA: last issue
             }
+            if (kind == FOP_ATTN && elect_one()) attention_mma(c, na);
             __syncwarp();
             cl_arrive();
             cl_wait();
         }
+        if (kind == FOP_ATTN) na += att_rounds(c);
         if (kind == FOP_GEMM) {
             gst += ns;
             ga += kch;
