@@ -30,8 +30,8 @@ for n, c in zip(names, clk):
     print(f"{n:16s} {c:9.0f} cyc  {c / 1965.0:7.2f} us")
 fine = clk[len(names):]
 clk = clk[:len(names)]
-labels = ["A loaded(+LN)", "A stored", "first acc_full", "last acc_full", "epilogue done", "barrier passed", "mma: A kb0 ready", "mma: first W ready", "mma: last issue", "tma: first issue", "tma: last issue"]
+labels = ["A loaded(+LN) | att: Q loaded", "A stored | att: staged", "first acc_full | att: S done", "last acc_full | att: P written", "epilogue done | att: O written", "barrier passed", "mma: A kb0 ready | att: O done", "mma: first W ready", "mma: last issue", "tma: first issue", "tma: last issue"]
 print(f"fine stamps of op {DBG_OP} ({names[DBG_OP]}), cycles since op start:")
 for l, v in zip(labels, fine):
-    print(f"   {l:20s} {v:9.0f}")
+    print(f"   {l:46s} {v:9.0f}")
 print(f"{'total':16s} {clk.sum():9.0f} cyc  {clk.sum() / 1965.0:7.2f} us   (B={B} T={T})")

@@ -38,7 +38,7 @@ static_assert(8 * 128 * 128 == kUniBytes && 4 * 32 * kStgPitch * 4 <= 4 * 128 * 
 // TMEM columns: A hi plane [0,128), A lo plane [128,256) (bf16x2 per column, K = 256), accumulators [256,512)
 constexpr uint32_t kTmALo = 128, kTmAcc = 256;
 constexpr int kAccSlots = 4;                          // 4 x 64 accumulator columns
-constexpr int kSmemF = kWStages * 2 * kWTile + kUniBytes + 256 + 1024;
+constexpr int kSmemF = kWStages * 2 * kWTile + kUniBytes + 256 /*barriers*/ + 256 /*two op slots*/ + 1024;
 static_assert(40 + 16 * kWStages + 16 * kAccSlots + 8 + 48 <= 256, "barrier block too small");
 constexpr int kKPitch = 68;                           // attention: K rows in smem (float4 reads, conflict free per quarter warp)
 
@@ -77,6 +77,7 @@ __device__ __forceinline__ void fwait(uint32_t bar, uint32_t parity, int tag, in
 struct Ctx {
     uint32_t wbase, bars, tmem_base;
     float* uni;            // union region (generic pointer)
+    FOpFields* opslot;     // two shared-memory slots: fields of the current / next op
     int tid, warp, lane;
     int b, r;              // stream index in the batch, CTA rank in the cluster
     int m0, rows;          // first global row and valid rows of this CTA's M tile
@@ -163,7 +164,7 @@ __device__ __forceinline__ void stage_to_tmem(const Ctx& c, const float4 (&v)[4]
 // through a [32 rows][64] staging tile shared by the two warps of the quadrant: thread l then owns row 32q + l,
 // columns 32hf + [0,32) of the k-block, splits them into bf16 hi / lo pairs and stores 16 + 16 packed columns.
 template <bool LN>
-__device__ __forceinline__ void gemm_workers(const Ctx& c, const FOp& op, int n_begin, int ns, int gst, int ga, long long* d2) {
+__device__ __forceinline__ void gemm_workers(const Ctx& c, const FOpFields& op, int n_begin, int ns, int gst, int ga, long long* d2) {
     const int kch = op.K >> 8;
     const int q = c.warp & 3, hf = c.warp >> 2, lg = c.lane >> 3, chunk = c.lane & 7;
     float* stg = c.uni + q * (2 * kStgFloats);
@@ -189,7 +190,8 @@ __device__ __forceinline__ void gemm_workers(const Ctx& c, const FOp& op, int n_
             }
         }
         if constexpr (LN) {
-            float mean[4], rstd[4];
+            // LayerNorm(256) of the 4 rows this thread shares with its 8-lane group: two-pass statistics,
+            // deviations kept in place, y = (x - mean) * rstd * w + b
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float sum = 0.f;
@@ -200,20 +202,29 @@ __device__ __forceinline__ void gemm_workers(const Ctx& c, const FOp& op, int n_
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-                mean[i] = sum * (1.0f / 256.0f);
-                float sq = 0.f;
+                const float mean = sum * (1.0f / 256.0f);
+                float sq0 = 0.f, sq1 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float d[8] = {vr[j][i][0].x - mean[i], vr[j][i][0].y - mean[i], vr[j][i][0].z - mean[i],
-                                        vr[j][i][0].w - mean[i], vr[j][i][1].x - mean[i], vr[j][i][1].y - mean[i],
-                                        vr[j][i][1].z - mean[i], vr[j][i][1].w - mean[i]};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) sq = fmaf(d[e], d[e], sq);
+                    float4& a = vr[j][i][0];
+                    float4& b = vr[j][i][1];
+                    a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
+                    b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
+                    sq0 = fmaf(a.x, a.x, sq0); sq1 = fmaf(a.y, a.y, sq1); sq0 = fmaf(a.z, a.z, sq0); sq1 = fmaf(a.w, a.w, sq1);
+                    sq0 = fmaf(b.x, b.x, sq0); sq1 = fmaf(b.y, b.y, sq1); sq0 = fmaf(b.z, b.z, sq0); sq1 = fmaf(b.w, b.w, sq1);
                 }
+                float sq = sq0 + sq1;
                 sq += __shfl_xor_sync(0xffffffffu, sq, 1);
                 sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                 sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                rstd[i] = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-5f);
+                const float rstd = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-5f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4& a = vr[j][i][0];
+                    float4& b = vr[j][i][1];
+                    a.x *= rstd; a.y *= rstd; a.z *= rstd; a.w *= rstd;
+                    b.x *= rstd; b.y *= rstd; b.z *= rstd; b.w *= rstd;
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -225,10 +236,8 @@ __device__ __forceinline__ void gemm_workers(const Ctx& c, const FOp& op, int n_
                 for (int i = 0; i < 4; ++i) {
                     float4& a = vr[j][i][0];
                     float4& b = vr[j][i][1];
-                    a.x = (a.x - mean[i]) * rstd[i] * w0.x + b0.x; a.y = (a.y - mean[i]) * rstd[i] * w0.y + b0.y;
-                    a.z = (a.z - mean[i]) * rstd[i] * w0.z + b0.z; a.w = (a.w - mean[i]) * rstd[i] * w0.w + b0.w;
-                    b.x = (b.x - mean[i]) * rstd[i] * w1.x + b1.x; b.y = (b.y - mean[i]) * rstd[i] * w1.y + b1.y;
-                    b.z = (b.z - mean[i]) * rstd[i] * w1.z + b1.z; b.w = (b.w - mean[i]) * rstd[i] * w1.w + b1.w;
+                    a.x = fmaf(a.x, w0.x, b0.x); a.y = fmaf(a.y, w0.y, b0.y); a.z = fmaf(a.z, w0.z, b0.z); a.w = fmaf(a.w, w0.w, b0.w);
+                    b.x = fmaf(b.x, w1.x, b1.x); b.y = fmaf(b.y, w1.y, b1.y); b.z = fmaf(b.z, w1.z, b1.z); b.w = fmaf(b.w, w1.w, b1.w);
                 }
             }
         }
@@ -335,7 +344,7 @@ __device__ __forceinline__ void att_store_planes(const Ctx& c, const float4 (&v)
 
 __device__ __forceinline__ int att_rounds(const Ctx& c) { return c.mode == 0 ? 1 : 2; }
 
-__device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op, int na) {
+__device__ __forceinline__ void attention_workers(const Ctx& c, const FOpFields& op, int na, long long* d2) {
     const AttMap am{c.mode, c.b, c.r, c.T};
     const int q = c.warp & 3, x = c.warp >> 2;             // softmax / epilogue: quadrant q of head x
     const uint32_t tm_q = c.tmem_base + ((uint32_t)(q * 32) << 16);
@@ -345,31 +354,37 @@ __device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op, i
     for (int round = 0; round < att_rounds(c); ++round) {
         const uint32_t par = (uint32_t)(na + round) & 1u;
         const int hbase = c.mode == 0 ? 2 * c.r : 2 * round;
-        // ---- stage Q (tensor memory), K and V (shared memory) of both heads
+        // ---- stage Q (tensor memory), K and V (shared memory) of both heads; the loads of the next tensor are in
+        //      flight while the previous one is converted
         {
-            float4 v[2][4][2];
+            float4 va[2][4][2], vb[2][4][2];
 #pragma unroll
-            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.Q, op.ldq, hbase + hx, 0, c.t, v[hx]);
+            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.Q, op.ldq, hbase + hx, 0, c.t, va[hx]);
+#pragma unroll
+            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.Kp, op.ldk, hbase + hx, op.sibling, c.t, vb[hx]);
+            if (d2) {
+                asm volatile("" ::"f"(va[1][3][1].w));
+                d2[1] = clock64();             // Q loads landed
+            }
 #pragma unroll
             for (int hx = 0; hx < 2; ++hx) {
                 if (hx) pair_sync(q);          // the partner warp has read head 0 out of the staging tile
-                stage_to_tmem(c, v[hx], stg, tm_q + kTmQ + 64u * hx, tm_q + kTmQ + 64u * hx + 32u);
+                stage_to_tmem(c, va[hx], stg, tm_q + kTmQ + 64u * hx, tm_q + kTmQ + 64u * hx + 32u);
             }
 #pragma unroll
-            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.Kp, op.ldk, hbase + hx, op.sibling, c.t, v[hx]);
+            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.V, op.ldv, hbase + hx, op.sibling, c.t, va[hx]);
 #pragma unroll
-            for (int hx = 0; hx < 2; ++hx) att_store_planes(c, v[hx], ub + hx * 2 * kAttPlane, ub + hx * 2 * kAttPlane + kAttPlane);
+            for (int hx = 0; hx < 2; ++hx) att_store_planes(c, vb[hx], ub + hx * 2 * kAttPlane, ub + hx * 2 * kAttPlane + kAttPlane);
             workers_sync();                    // every warp is past the Q staging tiles, which alias the V planes
 #pragma unroll
-            for (int hx = 0; hx < 2; ++hx) att_load_rows(c, am, op.V, op.ldv, hbase + hx, op.sibling, c.t, v[hx]);
-#pragma unroll
             for (int hx = 0; hx < 2; ++hx)
-                att_store_planes(c, v[hx], ub + (4 + 2 * hx) * kAttPlane, ub + (5 + 2 * hx) * kAttPlane);
+                att_store_planes(c, va[hx], ub + (4 + 2 * hx) * kAttPlane, ub + (5 + 2 * hx) * kAttPlane);
             fence_proxy_async();
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (c.lane == 0) mbar_arrive(c.att_in());
+            if (d2) d2[2] = clock64();         // Q / K / V staged
         }
         // ---- softmax of head x, rows of quadrant q: thread = row
         {
@@ -383,6 +398,7 @@ __device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op, i
             const uint32_t tS = tm_q + kTmS + 128u * x;
             fwait(c.s_full(), par, 7, c.oi);
             tc_fence_after();
+            if (d2) d2[3] = clock64();         // S complete
             float m = -INFINITY, l = 0.f;
             for (int cc = 0; cc < nch; ++cc) {
                 uint32_t raw[32];
@@ -399,8 +415,8 @@ __device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op, i
                 float acc = 0.f;
                 if (mn > -INFINITY) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) acc += expf(__uint_as_float(raw[e]) - mn);
-                    l = l * expf(m - mn) + acc;
+                    for (int e = 0; e < 32; ++e) acc += __expf(__uint_as_float(raw[e]) - mn);
+                    l = l * __expf(m - mn) + acc;
                 }
                 m = mn;
             }
@@ -415,8 +431,8 @@ __device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op, i
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int j0 = 32 * lc + 2 * e, j1 = j0 + 1;
-                        const float p0 = (rowv && j0 <= i) ? expf(__uint_as_float(raw[2 * e]) * 0.0625f + slope * (float)j0 - mm) * inv : 0.f;
-                        const float p1 = (rowv && j1 <= i) ? expf(__uint_as_float(raw[2 * e + 1]) * 0.0625f + slope * (float)j1 - mm) * inv : 0.f;
+                        const float p0 = (rowv && j0 <= i) ? __expf(__uint_as_float(raw[2 * e]) * 0.0625f + slope * (float)j0 - mm) * inv : 0.f;
+                        const float p1 = (rowv && j1 <= i) ? __expf(__uint_as_float(raw[2 * e + 1]) * 0.0625f + slope * (float)j1 - mm) * inv : 0.f;
                         split2(p0, p1, hi[e], lo[e]);
                     }
                 } else {
@@ -430,11 +446,13 @@ __device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op, i
             tc_fence_before();
             __syncwarp();
             if (c.lane == 0) mbar_arrive(c.p_ready(x));
+            if (d2) d2[4] = clock64();         // P written
         }
         // ---- O of head x, rows of quadrant q -> global
         {
             fwait(c.o_full(x), par, 8, c.oi);
             tc_fence_after();
+            if (d2) d2[7] = clock64();         // O complete
             const int seq = c.mode == 0 ? 2 * c.b + (q >> 1) : 2 * c.b + c.r;
             const int i0 = c.mode == 0 ? 32 * (q & 1) : 32 * q;
             const int rows_valid = min(32, c.T - i0);
@@ -446,6 +464,7 @@ __device__ __forceinline__ void attention_workers(const Ctx& c, const FOp& op, i
                 tmem_ld32(tm_q + kTmO + 64u * x + 32u * half, raw);
                 epi_block<false, false>(raw, tbuf, c.lane, rows_valid, nullptr, Cb, op.ldo, (hbase + x) * 64 + 32 * half);
             }
+            if (d2) d2[5] = clock64();         // O written
         }
         if (round + 1 < att_rounds(c)) {
             tc_fence_before();
@@ -481,21 +500,28 @@ __device__ __forceinline__ void attention_mma(const Ctx& c, int na) {
             }
         }
         umma_commit(c.s_full());
-        for (int hx = 0; hx < 2; ++hx) {
-            fwait(c.p_ready(hx), par, 10, c.oi);
-            tc_fence_after();
-            const uint32_t acc = c.tmem_base + kTmO + 64u * hx;
-            const uint32_t vh = ub + (4 + 2 * hx) * kAttPlane, vl = vh + kAttPlane;
-            for (int kk = 0; kk < nk; ++kk) {
-                // keys [16 kk, +16): chunk kk / 2, half kk % 2 -> 8 packed columns of the hi and of the lo half of the chunk
-                const uint32_t ph = c.tmem_base + kTmS + 128u * hx + 32u * (kk >> 1) + 8u * (kk & 1), pl = ph + 16u;
-                const uint32_t voff = (uint32_t)kk * 2048u;        // 16 key rows of 128 bytes
-                umma_bf16_ta(acc, pl, make_desc(vh + voff), idesc_o, kk ? 1u : 0u);
-                umma_bf16_ta(acc, ph, make_desc(vl + voff), idesc_o, 1u);
-                umma_bf16_ta(acc, ph, make_desc(vh + voff), idesc_o, 1u);
+        fwait(c.p_ready(0), par, 10, c.oi);
+        fwait(c.p_ready(1), par, 10, c.oi);
+        tc_fence_after();
+        for (int kk = 0; kk < nk; ++kk) {
+            // keys [16 kk, +16): chunk kk / 2, half kk % 2 -> 8 packed columns of the hi and of the lo half of the chunk;
+            // the two heads alternate so that dependent MMAs on one accumulator are not back to back
+            const uint32_t voff = (uint32_t)kk * 2048u;        // 16 key rows of 128 bytes
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                for (int hx = 0; hx < 2; ++hx) {
+                    const uint32_t acc = c.tmem_base + kTmO + 64u * hx;
+                    const uint32_t vh = ub + (4 + 2 * hx) * kAttPlane + voff, vl = vh + kAttPlane;
+                    const uint32_t ph = c.tmem_base + kTmS + 128u * hx + 32u * (kk >> 1) + 8u * (kk & 1), pl = ph + 16u;
+                    if (prod == 0) umma_bf16_ta(acc, pl, make_desc(vh), idesc_o, kk ? 1u : 0u);
+                    else if (prod == 1) umma_bf16_ta(acc, ph, make_desc(vl), idesc_o, 1u);
+                    else umma_bf16_ta(acc, ph, make_desc(vh), idesc_o, 1u);
+                }
             }
-            umma_commit(c.o_full(hx));
         }
+        umma_commit(c.o_full(0));
+        umma_commit(c.o_full(1));
     }
 }
 
@@ -505,6 +531,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
     c.wbase = (smem_u32(smem_raw) + 1023u) & ~1023u;       // W ring first: SWIZZLE_128B tiles need 1024 B alignment
     c.uni = reinterpret_cast<float*>(smem_raw + (c.wbase - smem_u32(smem_raw)) + kWStages * 2 * kWTile);
     c.bars = c.wbase + kWStages * 2 * kWTile + kUniBytes;
+    c.opslot = reinterpret_cast<FOpFields*>(reinterpret_cast<uint8_t*>(c.uni) + kUniBytes + 256);
     c.tid = threadIdx.x;
     c.warp = c.tid >> 5;
     c.lane = c.tid & 31;
@@ -538,6 +565,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
         fence_barrier_init();
     }
     if (c.warp == kWorkers + 1) tmem_alloc(c.tmem_slot(), 512u);
+    if (c.warp == 0) reinterpret_cast<uint32_t*>(c.opslot)[c.lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ops[0].f) + c.lane);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -547,8 +575,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && c.tid == 0;
 
     for (int oi = 0; oi < p.n_ops; ++oi) {
-        const FOp& op = p.ops[oi];
+        // the workers and the MMA warp read the op from shared memory (copied one op ahead, visible through the
+        // cluster barrier); the TMA warp runs ahead of that copy and reads the three fields it needs from global
+        const bool is_tma = c.warp == kWorkers;
+        const FOpFields& op = is_tma ? p.ops[oi].f : c.opslot[oi & 1];
         c.oi = oi;
+        if (c.warp == kWorkers + 1 && oi + 1 < p.n_ops)
+            reinterpret_cast<uint32_t*>(&c.opslot[(oi + 1) & 1])[c.lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ops[oi + 1].f) + c.lane);
         const int kind = __shfl_sync(0xffffffffu, op.kind, 0);
         if (dbg) p.dbg[oi] = clock64();
         // fine stamps of one op (p.dbg_op) of cluster 0 / CTA 0: slots 40.. of the clock buffer
@@ -570,7 +603,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
                 if (op.ln_w) gemm_workers<true>(c, op, n_begin, ns, gst, ga, c.tid == 0 ? d2 : nullptr);
                 else gemm_workers<false>(c, op, n_begin, ns, gst, ga, c.tid == 0 ? d2 : nullptr);
             } else if (kind == FOP_ATTN) {
-                attention_workers(c, op, na);
+                attention_workers(c, op, na, c.tid == 0 ? d2 : nullptr);
             } else if (kind == FOP_GATHER_RING) {
                 // X rows of channel r = ring rows oldest first, zero rows above t (vap_main.py:274-283)
                 const int ch = c.r;
@@ -625,8 +658,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
                                 const uint32_t ph = (uint32_t)(w / kWStages) & 1u;
                                 fwait(c.w_empty(s), ph ^ 1u, 3, c.oi);
                                 mbar_arrive_expect_tx(c.w_full(s), 2u * kWTile);
-                                tma_load_2d(c.w_hi(s), &op.map_hi, kc * 256 + kb * kBK, n_begin + (sp + sub) * 64, c.w_full(s));
-                                tma_load_2d(c.w_lo(s), &op.map_lo, kc * 256 + kb * kBK, n_begin + (sp + sub) * 64, c.w_full(s));
+                                tma_load_2d(c.w_hi(s), &p.ops[oi].map_hi, kc * 256 + kb * kBK, n_begin + (sp + sub) * 64, c.w_full(s));
+                                tma_load_2d(c.w_lo(s), &p.ops[oi].map_lo, kc * 256 + kb * kBK, n_begin + (sp + sub) * 64, c.w_full(s));
                             }
                 if (d2) d2[11] = clock64();            // TMA: last issue
             }

@@ -18,8 +18,7 @@ namespace vapb {
 
 enum FOpKind { FOP_GEMM = 0, FOP_ATTN = 1, FOP_GATHER_RING = 2, FOP_VAD = 3, FOP_GATHER_LAST = 4 };
 
-struct alignas(64) FOp {
-    CUtensorMap map_hi, map_lo;      // W planes, box {64 k, 64 n}, SWIZZLE_128B (GEMM only)
+struct FOpFields {                   // 128 bytes: copied to shared memory one op ahead
     int kind;
     // GEMM: C[rows, N] = act(LN?(A[rows, K]) W^T) + R      (R and C share ldc; R may alias C)
     int K, N, act, lda, ldc;
@@ -37,6 +36,11 @@ struct alignas(64) FOp {
     float* O;
     const float* slopes;
 };
+struct alignas(64) FOp {
+    CUtensorMap map_hi, map_lo;      // W planes, box {64 k, 64 n}, SWIZZLE_128B (GEMM only)
+    FOpFields f;
+};
+static_assert(sizeof(FOpFields) == 128 && sizeof(FOp) == 384, "FOp layout");
 
 struct FusedParams {
     const FOp* ops;

@@ -308,7 +308,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
         if (dbg && tid == 0) dbg[3] = clock64();          // epilogue of warp 0 done
     } else if (warp == kProducerWarps) {
         // ================= TMA producer (W planes) =================
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % C::kStages;
                 const uint32_t ph = (uint32_t)(kb / C::kStages) & 1u;
@@ -321,7 +321,7 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
         }
     } else {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(BN);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % C::kStages;
@@ -514,7 +514,7 @@ k_gemm_tc_k256(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, con
         }
     } else if (warp == kProducerWarps) {
         // ================= TMA producer: W planes of every (subtile, k-block) =================
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0;
             for (int st = 0; st < ns; ++st) {
                 for (int kb = 0; kb < 4; ++kb, ++it) {
@@ -537,7 +537,7 @@ k_gemm_tc_k256(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, con
         }
     } else {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(64);
             int it = 0;
             for (int st = 0; st < ns; ++st) {

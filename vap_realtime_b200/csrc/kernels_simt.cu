@@ -8,6 +8,8 @@
 // Reference semantics restated per kernel (file:line under the reference tree).
 #include "common.cuh"
 
+#include <cstdlib>
+
 #include <math.h>
 
 namespace vapb {
@@ -588,8 +590,11 @@ void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* 
         cudaFuncSetAttribute(k_lstm_recurrent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<8>());
         cudaFuncSetAttribute(k_lstm_recurrent<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<16>());
     }
-    // 8-row tiles while that still fits one wave of clusters (more SMs busy), 16-row tiles for big batches
-    if ((NC + 7) / 8 * 8 <= 144) {
+    // 8-row tiles only for small batches: 16 clusters of 8 CTAs do not fit one wave on every B200 (GPCs with fewer
+    // than 16 free SMs take one cluster, not two), and a second wave doubles the kernel (measured: 16-row tiles
+    // are 22 us faster at NC = 128, profiles/r01_m_lstm_tiles.log)
+    static const int force_rt = getenv("VAPB_LSTM_RT") ? atoi(getenv("VAPB_LSTM_RT")) : 0;      // experiment knob
+    if (force_rt != 16 && (force_rt == 8 || NC <= 64)) {
         const int tiles = (NC + 7) / 8;
         launch_k(k_lstm_recurrent<8>, dim3(tiles * 8), dim3(256), lstm_smem<8>(), st, Gx, Whh, hS, cS, ids, Y, NC, n_steps);
     } else {

@@ -461,23 +461,23 @@ FOp fop_gemm(const float* A, int lda, int K, const TcWeight& w, const float* ln_
              int ldc, int N, int act) {
     FOp o;
     memset(&o, 0, sizeof o);
-    o.kind = FOP_GEMM;
+    o.f.kind = FOP_GEMM;
     o.map_hi = w.map_hi[0];
     o.map_lo = w.map_lo[0];
-    o.A = A; o.lda = lda; o.K = K; o.ln_w = ln_w; o.ln_b = ln_b; o.R = R; o.C = C; o.ldc = ldc; o.N = N; o.act = act;
+    o.f.A = A; o.f.lda = lda; o.f.K = K; o.f.ln_w = ln_w; o.f.ln_b = ln_b; o.f.R = R; o.f.C = C; o.f.ldc = ldc; o.f.N = N; o.f.act = act;
     return o;
 }
 FOp fop_attn(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O, const float* slopes, int sibling) {
     FOp o;
     memset(&o, 0, sizeof o);
-    o.kind = FOP_ATTN;
-    o.Q = Q; o.ldq = ldq; o.Kp = K; o.ldk = ldk; o.V = V; o.ldv = ldv; o.O = O; o.ldo = kD; o.slopes = slopes; o.sibling = sibling;
+    o.f.kind = FOP_ATTN;
+    o.f.Q = Q; o.f.ldq = ldq; o.f.Kp = K; o.f.ldk = ldk; o.f.V = V; o.f.ldv = ldv; o.f.O = O; o.f.ldo = kD; o.f.slopes = slopes; o.f.sibling = sibling;
     return o;
 }
 FOp fop_misc(int kind) {
     FOp o;
     memset(&o, 0, sizeof o);
-    o.kind = kind;
+    o.f.kind = kind;
     return o;
 }
 
