@@ -30,7 +30,7 @@ for n, c in zip(names, clk):
     print(f"{n:16s} {c:9.0f} cyc  {c / 1965.0:7.2f} us")
 fine = clk[len(names):]
 clk = clk[:len(names)]
-labels = ["A loaded(+LN) | att: Q loaded", "A stored | att: staged", "first acc_full | att: S done", "last acc_full | att: P written", "epilogue done | att: O written", "barrier passed", "mma: A kb0 ready | att: O done", "mma: first W ready", "mma: last issue", "tma: first issue", "tma: last issue"]
+labels = ["A loaded(+LN) | att: Q loaded", "A stored | att: staged", "first acc_full | att: S done", "last acc_full | att: P written", "epilogue done | att: O written", "barrier passed", "mma: A kb0 ready | att: O done", "mma: first W ready", "mma: last issue", "tma: first issue", "tma: last issue", "A loads landed (before LN)"]
 print(f"fine stamps of op {DBG_OP} ({names[DBG_OP]}), cycles since op start:")
 for l, v in zip(labels, fine):
     print(f"   {l:46s} {v:9.0f}")

@@ -23,7 +23,7 @@ namespace {
 using namespace tcp;
 
 constexpr int kWorkers = 8;
-constexpr int kThreadsF = (kWorkers + 2) * 32;
+constexpr int kThreadsF = (kWorkers + 4) * 32;        // 8 workers + TMA + MMA + 2 spare warps (three full warpgroups)
 #ifndef VAPB_F_WSTAGES
 #define VAPB_F_WSTAGES 6
 #endif
@@ -60,17 +60,21 @@ __device__ __forceinline__ float warp_max_f(float v) {
     return v;
 }
 
-// bounded mbarrier wait that names what it was waiting for (a mis-programmed pipeline must fail loudly, never hang)
+// bounded mbarrier wait that names what it was waiting for (a mis-programmed pipeline must fail loudly, never hang).
+// The failure path is a noreturn, non-inlined call: nothing is live across it, so the hot loops keep their registers
+// (with the printf inlined, ptxas parked loop state in local memory, and every cluster barrier invalidates L1).
+__device__ __noinline__ __attribute__((noreturn)) void fwait_fail(int tag, int oi, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0)
+        printf("vapb stream kernel: wait %d (1 a_empty 2 acc_full 3 w_empty 4 acc_empty 5 a_full 6 w_full 7 s_full 8 o_full 9 att_in 10 p_ready) timed out, op %d block %d warp %d parity %u\n",
+               tag, oi, blockIdx.x, threadIdx.x >> 5, parity);
+    __trap();
+    for (;;) {}
+}
 __device__ __forceinline__ void fwait(uint32_t bar, uint32_t parity, int tag, int oi) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 2000000000LL) {
-            if ((threadIdx.x & 31) == 0)
-                printf("vapb stream kernel: wait %d (1 a_empty 2 acc_full 3 w_empty 4 acc_empty 5 a_full 6 w_full 7 s_full 8 o_full 9 att_in 10 p_ready) timed out, op %d block %d warp %d parity %u\n",
-                       tag, oi, blockIdx.x, threadIdx.x >> 5, parity);
-            __trap();
-        }
+        if (clock64() - t0 > 2000000000LL) fwait_fail(tag, oi, parity);
     }
 }
 
@@ -525,6 +529,208 @@ __device__ __forceinline__ void attention_mma(const Ctx& c, int na) {
     }
 }
 
+// ---- op shape of this CTA (loaded values are shuffled so that the compiler knows they are warp-uniform) ----
+struct OpShape { int kind, ns, kch, n_begin; };
+__device__ __forceinline__ OpShape op_shape(const Ctx& c, const FOpFields& op) {
+    OpShape o;
+    o.kind = __shfl_sync(0xffffffffu, op.kind, 0);
+    o.ns = 0; o.kch = 0; o.n_begin = 0;
+    if (o.kind == FOP_GEMM) {
+        o.kch = op.K >> 8;
+        if (c.mode == 0) { o.ns = op.N >> 7; o.n_begin = c.r * (op.N >> 1); }
+        else { o.ns = op.N >> 6; }
+    }
+    o.ns = __shfl_sync(0xffffffffu, o.ns, 0);
+    o.kch = __shfl_sync(0xffffffffu, o.kch, 0);
+    o.n_begin = __shfl_sync(0xffffffffu, o.n_begin, 0);
+    return o;
+}
+__device__ __forceinline__ long long* fine_stamps(const FusedParams& p, int oi) {
+    // fine stamps of one op (p.dbg_op) of cluster 0 / CTA 0: slots 40.. of the clock buffer
+    return (p.dbg != nullptr && blockIdx.x == 0 && oi == p.dbg_op) ? p.dbg + 40 : nullptr;
+}
+
+// =========================== workers (warps 0-7) ===========================
+__device__ __forceinline__ void workers_loop(Ctx& c, const FusedParams& p, int id, int cnt) {
+    int gst = 0, ga = 0, na = 0;     // running counters: accumulator subtiles, A generations, attention rounds
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && c.tid == 0;
+    for (int oi = 0; oi < p.n_ops; ++oi) {
+        const FOpFields& op = c.opslot[oi & 1];      // copied one op ahead by the MMA warp, visible through the cluster barrier
+        c.oi = oi;
+        const OpShape sh = op_shape(c, op);
+        if (dbg) p.dbg[oi] = clock64();
+        long long* d2 = c.tid == 0 ? fine_stamps(p, oi) : nullptr;
+        if (d2) d2[0] = clock64();
+        if (sh.kind == FOP_GEMM) {
+            if (op.ln_w) gemm_workers<true>(c, op, sh.n_begin, sh.ns, gst, ga, d2);
+            else gemm_workers<false>(c, op, sh.n_begin, sh.ns, gst, ga, d2);
+            gst += sh.ns;
+            ga += sh.kch;
+        } else if (sh.kind == FOP_ATTN) {
+            attention_workers(c, op, na, d2);
+            na += att_rounds(c);
+        } else if (sh.kind == FOP_GATHER_RING) {
+            // X rows of channel r = ring rows oldest first, zero rows above t (vap_main.py:274-283)
+            const int ch = c.r;
+            const float* rg = p.ring + ((size_t)id * 2 + ch) * p.T * kD;
+            float* xo = p.X + (size_t)(2 * c.b + ch) * p.T * kD;
+            for (int i = c.tid; i < p.T * 64; i += kWorkers * 32) {
+                const int j = i >> 6, q = i & 63;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < c.t) {
+                    const int slot = (cnt - c.t + j) % p.T;
+                    v = ldcg4(rg + (size_t)slot * kD + 4 * q);
+                }
+                *reinterpret_cast<float4*>(xo + (size_t)j * kD + 4 * q) = v;
+            }
+            if (c.r == 0 && c.tid == 0) p.tvalid[c.b] = c.t;
+        } else if (sh.kind == FOP_VAD) {
+            // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
+            if (c.warp == 0) {
+                const float* xr = p.X + ((size_t)(2 * c.b + c.r) * p.T + (c.t - 1)) * kD + 8 * c.lane;
+                const float4 x0 = ldcg4(xr), x1 = ldcg4(xr + 4);
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane + 4));
+                float s = 0.f;
+                s = fmaf(x0.x, w0.x, s); s = fmaf(x0.y, w0.y, s); s = fmaf(x0.z, w0.z, s); s = fmaf(x0.w, w0.w, s);
+                s = fmaf(x1.x, w1.x, s); s = fmaf(x1.y, w1.y, s); s = fmaf(x1.z, w1.z, s); s = fmaf(x1.w, w1.w, s);
+                s = warp_sum_f(s) + __ldg(p.va_b);
+                if (c.lane == 0) p.out[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
+            }
+        } else if (sh.kind == FOP_GATHER_LAST) {
+            if (c.warp == 0) {
+                const int n = 2 * c.b + c.r;
+                const float* xr = p.X + ((size_t)n * p.T + (c.t - 1)) * kD + 8 * c.lane;
+                float* xo = p.Xl + (size_t)n * kD + 8 * c.lane;
+                *reinterpret_cast<float4*>(xo) = ldcg4(xr);
+                *reinterpret_cast<float4*>(xo + 4) = ldcg4(xr + 4);
+            }
+        }
+        cl_arrive();
+        cl_wait();
+        if (d2) d2[6] = clock64();   // cluster barrier passed
+    }
+    if (dbg) p.dbg[p.n_ops] = clock64();
+}
+
+// =========================== TMA producer (warp 8), one op ahead of the others ===========================
+__device__ __forceinline__ void tma_loop(Ctx& c, const FusedParams& p) {
+    int wi = 0;                      // running W stage counter
+    for (int oi = 0; oi < p.n_ops; ++oi) {
+        c.oi = oi;
+        // this warp runs ahead of the shared-memory copy of the op: it reads the fields it needs from global memory
+        const OpShape sh = op_shape(c, p.ops[oi].f);
+        long long* d2 = fine_stamps(p, oi);
+        if (sh.kind == FOP_GEMM && elect_one()) {
+            int w = wi;
+            if (d2) d2[10] = clock64();            // TMA: first issue of this op
+            // tile order = MMA order: subtiles go in PAIRS that are issued interleaved (see the MMA warp)
+            for (int kc = 0; kc < sh.kch; ++kc)
+                for (int sp = 0; sp < sh.ns; sp += 2)
+                    for (int kb = 0; kb < 4; ++kb)
+                        for (int sub = 0; sub < 2; ++sub, ++w) {
+                            const int s = w % kWStages;
+                            const uint32_t ph = (uint32_t)(w / kWStages) & 1u;
+                            fwait(c.w_empty(s), ph ^ 1u, 3, c.oi);
+                            mbar_arrive_expect_tx(c.w_full(s), 2u * kWTile);
+                            tma_load_2d(c.w_hi(s), &p.ops[oi].map_hi, kc * 256 + kb * kBK, sh.n_begin + (sp + sub) * 64, c.w_full(s));
+                            tma_load_2d(c.w_lo(s), &p.ops[oi].map_lo, kc * 256 + kb * kBK, sh.n_begin + (sp + sub) * 64, c.w_full(s));
+                        }
+            if (d2) d2[11] = clock64();            // TMA: last issue
+        }
+        wi += sh.ns * 4 * sh.kch;
+        __syncwarp();
+        if (oi > 0) cl_wait();
+        cl_arrive();
+    }
+    cl_wait();                       // this warp is one barrier behind
+}
+
+// =========================== MMA issuer (warp 9) ===========================
+__device__ __forceinline__ void mma_loop(Ctx& c, const FusedParams& p) {
+    int gst = 0, ga = 0, wi = 0, na = 0;
+    for (int oi = 0; oi < p.n_ops; ++oi) {
+        const FOpFields& op = c.opslot[oi & 1];
+        c.oi = oi;
+        if (oi + 1 < p.n_ops)        // fields of the next op -> the other shared-memory slot
+            reinterpret_cast<uint32_t*>(&c.opslot[(oi + 1) & 1])[c.lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ops[oi + 1].f) + c.lane);
+        const OpShape sh = op_shape(c, op);
+        long long* d2 = fine_stamps(p, oi);
+        if (sh.kind == FOP_GEMM && elect_one()) {
+            const uint32_t tmb = c.tmem_base;
+            constexpr uint32_t idesc = make_idesc(64);
+            int w = wi;
+            // An accumulator takes one dependent MMA per ~90 cycles whatever its width, a 128 x 64 x 16 MMA is
+            // 32 cycles of tensor work: two subtiles (two accumulators) are issued interleaved so that the pipe
+            // is not idle between dependent MMAs.
+            for (int kc = 0; kc < sh.kch; ++kc) {
+                for (int sp = 0; sp < sh.ns; sp += 2) {
+                    const int g0 = gst + sp, g1 = g0 + 1;
+                    const int slot0 = g0 & (kAccSlots - 1), slot1 = g1 & (kAccSlots - 1);
+                    if (kc == 0) {
+                        fwait(c.acc_empty(slot0), ((uint32_t)(g0 / kAccSlots) & 1u) ^ 1u, 4, c.oi);
+                        fwait(c.acc_empty(slot1), ((uint32_t)(g1 / kAccSlots) & 1u) ^ 1u, 4, c.oi);
+                        tc_fence_after();
+                    }
+                    const uint32_t tm_acc0 = tmb + kTmAcc + (uint32_t)(slot0 * 64);
+                    const uint32_t tm_acc1 = tmb + kTmAcc + (uint32_t)(slot1 * 64);
+                    for (int kb = 0; kb < 4; ++kb, w += 2) {
+                        const int s0 = w % kWStages, s1 = (w + 1) % kWStages;
+                        const uint32_t ph0 = (uint32_t)(w / kWStages) & 1u, ph1 = (uint32_t)((w + 1) / kWStages) & 1u;
+                        if (sp == 0) fwait(c.a_full(kb), (uint32_t)(ga + kc) & 1u, 5, c.oi);
+                        if (d2 && kc == 0 && sp == 0 && kb == 0) d2[7] = clock64();      // MMA: A k-block 0 ready
+                        fwait(c.w_full(s0), ph0, 6, c.oi);
+                        fwait(c.w_full(s1), ph1, 6, c.oi);
+                        tc_fence_after();
+                        if (d2 && kc == 0 && sp == 0 && kb == 0) d2[8] = clock64();      // MMA: first W stages ready
+#pragma unroll
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            const uint32_t koff = (uint32_t)k * kUmmaK * 2;
+                            const uint32_t ah = tmb + (uint32_t)(kb * 32 + k * 8), al = ah + kTmALo;
+                            const uint64_t wh0 = make_desc(c.w_hi(s0) + koff), wl0 = make_desc(c.w_lo(s0) + koff);
+                            const uint64_t wh1 = make_desc(c.w_hi(s1) + koff), wl1 = make_desc(c.w_lo(s1) + koff);
+                            const uint32_t first = (kc | kb | k) ? 1u : 0u;
+                            umma_bf16_ta(tm_acc0, al, wh0, idesc, first);      // small terms first
+                            umma_bf16_ta(tm_acc1, al, wh1, idesc, first);
+                            umma_bf16_ta(tm_acc0, ah, wl0, idesc, 1u);
+                            umma_bf16_ta(tm_acc1, ah, wl1, idesc, 1u);
+                            umma_bf16_ta(tm_acc0, ah, wh0, idesc, 1u);
+                            umma_bf16_ta(tm_acc1, ah, wh1, idesc, 1u);
+                        }
+                        umma_commit(c.w_empty(s0));
+                        umma_commit(c.w_empty(s1));
+                    }
+                    if (kc == sh.kch - 1) {
+                        umma_commit(c.acc_full(slot0));
+                        umma_commit(c.acc_full(slot1));
+                    }
+                }
+                umma_commit(c.a_empty());
+            }
+            if (d2) d2[9] = clock64();             // MMA: last issue
+        }
+        if (sh.kind == FOP_ATTN && elect_one()) attention_mma(c, na);
+        if (sh.kind == FOP_ATTN) na += att_rounds(c);
+        gst += sh.ns;
+        ga += sh.kch;
+        wi += sh.ns * 4 * sh.kch;
+        __syncwarp();
+        cl_arrive();
+        cl_wait();
+    }
+}
+
+// Warp-specialised register budgets (setmaxnreg, per warpgroup): the kernel launches with 168 registers per thread
+// (12 warps); the two worker warpgroups grow to 208 (they hold a 128 x 256 fp32 tile in registers), the TMA / MMA /
+// idle warpgroup shrinks to 88 (the pool only holds what the shrinking warps release: 8 x 40 = 4 x 80).  Each role runs its own copy of the op loop so that no code is shared between budgets.
+#ifndef VAPB_F_NO_SETMAXNREG
+__device__ __forceinline__ void reg_grow() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
+__device__ __forceinline__ void reg_shrink() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;"); }
+#else
+__device__ __forceinline__ void reg_grow() {}
+__device__ __forceinline__ void reg_shrink() {}
+#endif
+
 __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p) {
     extern __shared__ uint8_t smem_raw[];
     Ctx c;
@@ -539,6 +745,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
     c.b = blockIdx.x >> 1;
     c.T = p.T;
     c.mode = p.mode;
+    c.oi = 0;
     if (p.mode == 0) { c.m0 = c.b * 2 * p.T; c.rows = 2 * p.T; }
     else { c.m0 = (2 * c.b + c.r) * p.T; c.rows = p.T; }
     const int id = __ldg(p.ids + c.b);
@@ -571,171 +778,20 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
     tc_fence_after();
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c.tmem_base) : "r"(c.tmem_slot()));
 
-    int gst = 0, ga = 0, wi = 0, na = 0;     // running counters: accumulator subtiles, A generations, W stages, attention rounds
-    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && c.tid == 0;
-
-    for (int oi = 0; oi < p.n_ops; ++oi) {
-        // the workers and the MMA warp read the op from shared memory (copied one op ahead, visible through the
-        // cluster barrier); the TMA warp runs ahead of that copy and reads the three fields it needs from global
-        const bool is_tma = c.warp == kWorkers;
-        const FOpFields& op = is_tma ? p.ops[oi].f : c.opslot[oi & 1];
-        c.oi = oi;
-        if (c.warp == kWorkers + 1 && oi + 1 < p.n_ops)
-            reinterpret_cast<uint32_t*>(&c.opslot[(oi + 1) & 1])[c.lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ops[oi + 1].f) + c.lane);
-        const int kind = __shfl_sync(0xffffffffu, op.kind, 0);
-        if (dbg) p.dbg[oi] = clock64();
-        // fine stamps of one op (p.dbg_op) of cluster 0 / CTA 0: slots 40.. of the clock buffer
-        long long* d2 = (p.dbg != nullptr && blockIdx.x == 0 && oi == p.dbg_op) ? p.dbg + 40 : nullptr;
-        if (d2 && c.tid == 0) d2[0] = clock64();
-        int n_begin = 0, ns = 0, kch = 0;
-        if (kind == FOP_GEMM) {
-            kch = op.K >> 8;
-            if (c.mode == 0) { ns = op.N >> 7; n_begin = c.r * (op.N >> 1); }
-            else { ns = op.N >> 6; n_begin = 0; }
-        }
-        // loaded from global memory: tell the compiler they are warp-uniform (loop bounds of the MMA / TMA warps)
-        ns = __shfl_sync(0xffffffffu, ns, 0);
-        kch = __shfl_sync(0xffffffffu, kch, 0);
-        n_begin = __shfl_sync(0xffffffffu, n_begin, 0);
-        if (c.warp < kWorkers) {
-            // =========================== workers ===========================
-            if (kind == FOP_GEMM) {
-                if (op.ln_w) gemm_workers<true>(c, op, n_begin, ns, gst, ga, c.tid == 0 ? d2 : nullptr);
-                else gemm_workers<false>(c, op, n_begin, ns, gst, ga, c.tid == 0 ? d2 : nullptr);
-            } else if (kind == FOP_ATTN) {
-                attention_workers(c, op, na, c.tid == 0 ? d2 : nullptr);
-            } else if (kind == FOP_GATHER_RING) {
-                // X rows of channel r = ring rows oldest first, zero rows above t (vap_main.py:274-283)
-                const int ch = c.r;
-                const float* rg = p.ring + ((size_t)id * 2 + ch) * p.T * kD;
-                float* xo = p.X + (size_t)(2 * c.b + ch) * p.T * kD;
-                for (int i = c.tid; i < p.T * 64; i += kWorkers * 32) {
-                    const int j = i >> 6, q = i & 63;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j < c.t) {
-                        const int slot = (cnt - c.t + j) % p.T;
-                        v = ldcg4(rg + (size_t)slot * kD + 4 * q);
-                    }
-                    *reinterpret_cast<float4*>(xo + (size_t)j * kD + 4 * q) = v;
-                }
-                if (c.r == 0 && c.tid == 0) p.tvalid[c.b] = c.t;
-            } else if (kind == FOP_VAD) {
-                // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
-                if (c.warp == 0) {
-                    const float* xr = p.X + ((size_t)(2 * c.b + c.r) * p.T + (c.t - 1)) * kD + 8 * c.lane;
-                    const float4 x0 = ldcg4(xr), x1 = ldcg4(xr + 4);
-                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane));
-                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane + 4));
-                    float s = 0.f;
-                    s = fmaf(x0.x, w0.x, s); s = fmaf(x0.y, w0.y, s); s = fmaf(x0.z, w0.z, s); s = fmaf(x0.w, w0.w, s);
-                    s = fmaf(x1.x, w1.x, s); s = fmaf(x1.y, w1.y, s); s = fmaf(x1.z, w1.z, s); s = fmaf(x1.w, w1.w, s);
-                    s = warp_sum_f(s) + __ldg(p.va_b);
-                    if (c.lane == 0) p.out[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
-                }
-            } else if (kind == FOP_GATHER_LAST) {
-                if (c.warp == 0) {
-                    const int n = 2 * c.b + c.r;
-                    const float* xr = p.X + ((size_t)n * p.T + (c.t - 1)) * kD + 8 * c.lane;
-                    float* xo = p.Xl + (size_t)n * kD + 8 * c.lane;
-                    *reinterpret_cast<float4*>(xo) = ldcg4(xr);
-                    *reinterpret_cast<float4*>(xo + 4) = ldcg4(xr + 4);
-                }
+    if (c.warp < kWorkers) {
+        reg_grow();
+        workers_loop(c, p, id, cnt);
+    } else {
+        reg_shrink();
+        if (c.warp == kWorkers) tma_loop(c, p);
+        else if (c.warp == kWorkers + 1) mma_loop(c, p);
+        else {
+            for (int oi = 0; oi < p.n_ops; ++oi) {   // two spare warps complete the third warpgroup
+                cl_arrive();
+                cl_wait();
             }
-            cl_arrive();
-            cl_wait();
-            if (d2 && c.tid == 0) d2[6] = clock64();   // cluster barrier passed
-        } else if (c.warp == kWorkers) {
-            // =========================== TMA producer (one op ahead) ===========================
-            if (kind == FOP_GEMM && elect_one()) {
-                int w = wi;
-                if (d2) d2[10] = clock64();            // TMA: first issue of this op
-                // tile order = MMA order: subtiles go in PAIRS that are issued interleaved (see the MMA warp)
-                for (int kc = 0; kc < kch; ++kc)
-                    for (int sp = 0; sp < ns; sp += 2)
-                        for (int kb = 0; kb < 4; ++kb)
-                            for (int sub = 0; sub < 2; ++sub, ++w) {
-                                const int s = w % kWStages;
-                                const uint32_t ph = (uint32_t)(w / kWStages) & 1u;
-                                fwait(c.w_empty(s), ph ^ 1u, 3, c.oi);
-                                mbar_arrive_expect_tx(c.w_full(s), 2u * kWTile);
-                                tma_load_2d(c.w_hi(s), &p.ops[oi].map_hi, kc * 256 + kb * kBK, n_begin + (sp + sub) * 64, c.w_full(s));
-                                tma_load_2d(c.w_lo(s), &p.ops[oi].map_lo, kc * 256 + kb * kBK, n_begin + (sp + sub) * 64, c.w_full(s));
-                            }
-                if (d2) d2[11] = clock64();            // TMA: last issue
-            }
-            __syncwarp();
-            if (oi > 0) cl_wait();
-            cl_arrive();
-        } else {
-            // =========================== MMA issuer ===========================
-            if (kind == FOP_GEMM && elect_one()) {
-                const uint32_t lead = 1u;
-                const uint32_t tmb = c.tmem_base;
-                constexpr uint32_t idesc = make_idesc(64);
-                int w = wi;
-                // An accumulator takes one dependent MMA per ~90 cycles whatever its width, a 128 x 64 x 16 MMA is
-                // 32 cycles of tensor work: two subtiles (two accumulators) are issued interleaved so that the pipe
-                // is not idle between dependent MMAs (measured: 94 -> ~45 cycles per MMA).
-                for (int kc = 0; kc < kch; ++kc) {
-                    for (int sp = 0; sp < ns; sp += 2) {
-                        const int g0 = gst + sp, g1 = g0 + 1;
-                        const int slot0 = g0 & (kAccSlots - 1), slot1 = g1 & (kAccSlots - 1);
-                        if (kc == 0) {
-                            fwait(c.acc_empty(slot0), ((uint32_t)(g0 / kAccSlots) & 1u) ^ 1u, 4, c.oi);
-                            fwait(c.acc_empty(slot1), ((uint32_t)(g1 / kAccSlots) & 1u) ^ 1u, 4, c.oi);
-                            tc_fence_after();
-                        }
-                        const uint32_t tm_acc0 = tmb + kTmAcc + (uint32_t)(slot0 * 64);
-                        const uint32_t tm_acc1 = tmb + kTmAcc + (uint32_t)(slot1 * 64);
-                        for (int kb = 0; kb < 4; ++kb, w += 2) {
-                            const int s0 = w % kWStages, s1 = (w + 1) % kWStages;
-                            const uint32_t ph0 = (uint32_t)(w / kWStages) & 1u, ph1 = (uint32_t)((w + 1) / kWStages) & 1u;
-                            if (sp == 0) fwait(c.a_full(kb), (uint32_t)(ga + kc) & 1u, 5, c.oi);
-                            if (d2 && lead && kc == 0 && sp == 0 && kb == 0) d2[7] = clock64();      // MMA: A k-block 0 ready
-                            fwait(c.w_full(s0), ph0, 6, c.oi);
-                            fwait(c.w_full(s1), ph1, 6, c.oi);
-                            tc_fence_after();
-                            if (d2 && lead && kc == 0 && sp == 0 && kb == 0) d2[8] = clock64();      // MMA: first W stages ready
-#pragma unroll
-                            for (int k = 0; k < kBK / kUmmaK; ++k) {
-                                const uint32_t koff = (uint32_t)k * kUmmaK * 2;
-                                const uint32_t ah = tmb + (uint32_t)(kb * 32 + k * 8), al = ah + kTmALo;
-                                const uint64_t wh0 = make_desc(c.w_hi(s0) + koff), wl0 = make_desc(c.w_lo(s0) + koff);
-                                const uint64_t wh1 = make_desc(c.w_hi(s1) + koff), wl1 = make_desc(c.w_lo(s1) + koff);
-                                const uint32_t first = (kc | kb | k) ? 1u : 0u;
-                                umma_bf16_ta_p(tm_acc0, al, wh0, idesc, first, lead);      // small terms first
-                                umma_bf16_ta_p(tm_acc1, al, wh1, idesc, first, lead);
-                                umma_bf16_ta_p(tm_acc0, ah, wl0, idesc, 1u, lead);
-                                umma_bf16_ta_p(tm_acc1, ah, wl1, idesc, 1u, lead);
-                                umma_bf16_ta_p(tm_acc0, ah, wh0, idesc, 1u, lead);
-                                umma_bf16_ta_p(tm_acc1, ah, wh1, idesc, 1u, lead);
-                            }
-                            umma_commit_p(c.w_empty(s0), lead);
-                            umma_commit_p(c.w_empty(s1), lead);
-                        }
-                        if (kc == kch - 1) {
-                            umma_commit_p(c.acc_full(slot0), lead);
-                            umma_commit_p(c.acc_full(slot1), lead);
-                        }
-                    }
-                    umma_commit_p(c.a_empty(), lead);
-                }
-                if (d2 && lead) d2[9] = clock64();             // MMA: last issue
-            }
-            if (kind == FOP_ATTN && elect_one()) attention_mma(c, na);
-            __syncwarp();
-            cl_arrive();
-            cl_wait();
-        }
-        if (kind == FOP_ATTN) na += att_rounds(c);
-        if (kind == FOP_GEMM) {
-            gst += ns;
-            ga += kch;
-            wi += ns * 4 * kch;
         }
     }
-    if (c.warp == kWorkers) cl_wait();          // the TMA warp is one barrier behind
-    if (dbg) p.dbg[p.n_ops] = clock64();
     tc_fence_before();
     __syncthreads();
     if (c.warp == kWorkers + 1) tmem_dealloc(c.tmem_base, 512u);

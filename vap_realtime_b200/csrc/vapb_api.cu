@@ -610,7 +610,9 @@ void enqueue_step(Step& s) {
         mark(s, "ln_gelu_ring");
     }
     const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
-    if (c->opt_gemm == 1 && c->opt_fused && prune && c->fops) {
+    // one cluster per stream: a win while all clusters are co-resident (2B <= SM count); bigger batches are served
+    // better by the batched per-op kernels, whose GEMM tiles are full (measured B = 128 / 256: r01_m_option_ablation.log)
+    if (c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (2 * B <= 148 || c->opt_fused == 2)) {
         // ---- ring gather, ar_channel, vad, cross layers 0-1 and the K/V of the pruned last layer: ONE launch,
         //      a cluster of two CTAs per stream (fused_tf.cu); then the newest-frame tail of the last layer
         fused_transformer(s);
@@ -1053,7 +1055,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "splitk") h->opt_splitk = value ? 1 : 0;
         else if (k == "conv4p") h->opt_conv4p = value & 3;
         else if (k == "cluster2") h->tcws.cluster2 = value ? 1 : 0;
-        else if (k == "fused") h->opt_fused = value ? 1 : 0;
+        else if (k == "fused") h->opt_fused = value;      // 0 off, 1 auto (one wave of clusters), 2 always
         else if (k == "fused_dbg") h->opt_fused_dbg = value;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
@@ -1124,7 +1126,7 @@ int vapb_debug_tensor(vapb_handle h, const char* name, float* host_out, size_t c
         CK(h, cudaMemcpy(clk.data(), h->fused_clk, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
         tmp.resize((size_t)h->n_fops);
         for (int i = 0; i < h->n_fops; ++i) tmp[i] = (float)(clk[i + 1] - clk[i]);
-        for (int i = 1; i < 12; ++i) tmp.push_back(clk[40 + i] ? (float)(clk[40 + i] - clk[40]) : 0.f);   // fine stamps of op fused_dbg - 1
+        for (int i = 1; i < 13; ++i) tmp.push_back(clk[40 + i] ? (float)(clk[40 + i] - clk[40]) : 0.f);   // fine stamps of op fused_dbg - 1
         n = tmp.size();
     } else if (k == "lstm_out") { src = h->Y; n = (size_t)NC * h->n_lstm * kD; }
     else if (k == "e") { src = h->ebuf; n = (size_t)NC * kD; }
