@@ -70,11 +70,13 @@ __device__ __noinline__ __attribute__((noreturn)) void fwait_fail(int tag, int o
     __trap();
     for (;;) {}
 }
+// The wait loop counts polls instead of reading the clock: CS2R shares the XU pipe with the bf16 conversions of the
+// worker warps (ncu: XU pipe 61 % busy, 5 % of all executed instructions were clock reads of spinning warps).
 __device__ __forceinline__ void fwait(uint32_t bar, uint32_t parity, int tag, int oi) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 2000000000LL) fwait_fail(tag, oi, parity);
+        if (++polls > 40000000u) fwait_fail(tag, oi, parity);      // each failed try_wait suspends the thread for a while: seconds
     }
 }
 
@@ -403,6 +405,48 @@ __device__ __forceinline__ void attention_workers(const Ctx& c, const FOpFields&
             fwait(c.s_full(), par, 7, c.oi);
             tc_fence_after();
             if (d2) d2[3] = clock64();         // S complete
+            if (nch <= 2) {
+                // at most 64 visible keys (always the case for T <= 64): the scores stay in registers, one pass
+                uint32_t r0[32], r1[32];
+                tmem_ld32(tS + 32u * cfirst, r0);
+                if (nch == 2) tmem_ld32(tS + 32u * (cfirst + 1), r1);
+                float m = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float s0 = (rowv && e <= i) ? __uint_as_float(r0[e]) * 0.0625f + slope * (float)e : -INFINITY;
+                    const float s1 = (nch == 2 && rowv && 32 + e <= i) ? __uint_as_float(r1[e]) * 0.0625f + slope * (float)(32 + e) : -INFINITY;
+                    r0[e] = __float_as_uint(s0);
+                    r1[e] = __float_as_uint(s1);
+                    m = fmaxf(m, fmaxf(s0, s1));
+                }
+                const float mm = (m > -INFINITY) ? m : 0.f;
+                float l = 0.f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float e0 = __expf(__uint_as_float(r0[e]) - mm);      // exp(-inf) = 0 for masked keys
+                    const float e1 = __expf(__uint_as_float(r1[e]) - mm);
+                    r0[e] = __float_as_uint(e0);
+                    r1[e] = __float_as_uint(e1);
+                    l += e0 + e1;
+                }
+                const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t hi[16], lo[16];
+                    const int lc = cc - cfirst;
+                    if (lc == 0) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) split2(__uint_as_float(r0[2 * e]) * inv, __uint_as_float(r0[2 * e + 1]) * inv, hi[e], lo[e]);
+                    } else if (lc == 1 && nch == 2) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) split2(__uint_as_float(r1[2 * e]) * inv, __uint_as_float(r1[2 * e + 1]) * inv, hi[e], lo[e]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) { hi[e] = 0u; lo[e] = 0u; }
+                    }
+                    tmem_st16(tS + 32u * cc, hi);
+                    tmem_st16(tS + 32u * cc + 16u, lo);
+                }
+            } else {
             float m = -INFINITY, l = 0.f;
             for (int cc = 0; cc < nch; ++cc) {
                 uint32_t raw[32];
@@ -445,6 +489,7 @@ __device__ __forceinline__ void attention_workers(const Ctx& c, const FOpFields&
                 }
                 tmem_st16(tS + 32u * cc, hi);
                 tmem_st16(tS + 32u * cc + 16u, lo);
+            }
             }
             tmem_st_wait();
             tc_fence_before();
