@@ -658,6 +658,8 @@ __device__ __forceinline__ void workers_loop(Ctx& c, const FusedParams& p, int i
     if (dbg) p.dbg[p.n_ops] = clock64();
 }
 
+__device__ __forceinline__ int group_size(int ns);
+
 // =========================== TMA producer (warp 8), one op ahead of the others ===========================
 __device__ __forceinline__ void tma_loop(Ctx& c, const FusedParams& p) {
     int wi = 0;                      // running W stage counter
@@ -669,11 +671,12 @@ __device__ __forceinline__ void tma_loop(Ctx& c, const FusedParams& p) {
         if (sh.kind == FOP_GEMM && elect_one()) {
             int w = wi;
             if (d2) d2[10] = clock64();            // TMA: first issue of this op
-            // tile order = MMA order: subtiles go in PAIRS that are issued interleaved (see the MMA warp)
+            // tile order = MMA order: subtiles go in GROUPS of 2 or 3 that are issued interleaved (see mma_gemm)
+            const int G = group_size(sh.ns);
             for (int kc = 0; kc < sh.kch; ++kc)
-                for (int sp = 0; sp < sh.ns; sp += 2)
+                for (int sp = 0; sp < sh.ns; sp += G)
                     for (int kb = 0; kb < 4; ++kb)
-                        for (int sub = 0; sub < 2; ++sub, ++w) {
+                        for (int sub = 0; sub < G; ++sub, ++w) {
                             const int s = w % kWStages;
                             const uint32_t ph = (uint32_t)(w / kWStages) & 1u;
                             fwait(c.w_empty(s), ph ^ 1u, 3, c.oi);
@@ -691,6 +694,64 @@ __device__ __forceinline__ void tma_loop(Ctx& c, const FusedParams& p) {
     cl_wait();                       // this warp is one barrier behind
 }
 
+// ---- GEMM, MMA side (one elected thread).  Dependent MMAs on ONE accumulator issue at most every ~90 cycles whatever
+// their width, while a 128 x 64 x 16 MMA is 32 cycles of tensor work: G subtiles (G accumulators) are issued interleaved
+// so that the pipe is not idle between dependent MMAs.  G = 3 was measured SLOWER than G = 2 for the 6-subtile ops
+// (32.5k vs 29.5k cycles): with 4 accumulator slots the second group of 3 waits for the epilogue of the first.
+__device__ __forceinline__ int group_size(int ns) { return 2; }
+
+template <int G>
+__device__ __forceinline__ void mma_gemm(const Ctx& c, const OpShape& sh, int gst, int ga, int wi, long long* d2) {
+    const uint32_t tmb = c.tmem_base;
+    constexpr uint32_t idesc = make_idesc(64);
+    int w = wi;
+    for (int kc = 0; kc < sh.kch; ++kc) {
+        for (int sp = 0; sp < sh.ns; sp += G) {
+            uint32_t tm_acc[G];
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const int g = gst + sp + u, slot = g & (kAccSlots - 1);
+                tm_acc[u] = tmb + kTmAcc + (uint32_t)(slot * 64);
+                if (kc == 0) fwait(c.acc_empty(slot), ((uint32_t)(g / kAccSlots) & 1u) ^ 1u, 4, c.oi);
+            }
+            tc_fence_after();
+            for (int kb = 0; kb < 4; ++kb, w += G) {
+                if (sp == 0) fwait(c.a_full(kb), (uint32_t)(ga + kc) & 1u, 5, c.oi);
+                if (d2 && kc == 0 && sp == 0 && kb == 0) d2[7] = clock64();      // MMA: A k-block 0 ready
+                uint32_t wsm[G];
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const int s = (w + u) % kWStages;
+                    wsm[u] = c.w_hi(s);
+                    fwait(c.w_full(s), (uint32_t)((w + u) / kWStages) & 1u, 6, c.oi);
+                }
+                tc_fence_after();
+                if (d2 && kc == 0 && sp == 0 && kb == 0) d2[8] = clock64();      // MMA: first W stages ready
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                    const uint32_t koff = (uint32_t)k * kUmmaK * 2;
+                    const uint32_t ah = tmb + (uint32_t)(kb * 32 + k * 8), al = ah + kTmALo;
+                    const uint32_t first = (kc | kb | k) ? 1u : 0u;
+#pragma unroll
+                    for (int u = 0; u < G; ++u) umma_bf16_ta(tm_acc[u], al, make_desc(wsm[u] + koff), idesc, first);      // small terms first
+#pragma unroll
+                    for (int u = 0; u < G; ++u) umma_bf16_ta(tm_acc[u], ah, make_desc(wsm[u] + kWTile + koff), idesc, 1u);
+#pragma unroll
+                    for (int u = 0; u < G; ++u) umma_bf16_ta(tm_acc[u], ah, make_desc(wsm[u] + koff), idesc, 1u);
+                }
+#pragma unroll
+                for (int u = 0; u < G; ++u) umma_commit(c.w_empty((w + u) % kWStages));
+            }
+            if (kc == sh.kch - 1) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) umma_commit(c.acc_full((gst + sp + u) & (kAccSlots - 1)));
+            }
+        }
+        umma_commit(c.a_empty());
+    }
+    if (d2) d2[9] = clock64();             // MMA: last issue
+}
+
 // =========================== MMA issuer (warp 9) ===========================
 __device__ __forceinline__ void mma_loop(Ctx& c, const FusedParams& p) {
     int gst = 0, ga = 0, wi = 0, na = 0;
@@ -702,57 +763,8 @@ __device__ __forceinline__ void mma_loop(Ctx& c, const FusedParams& p) {
         const OpShape sh = op_shape(c, op);
         long long* d2 = fine_stamps(p, oi);
         if (sh.kind == FOP_GEMM && elect_one()) {
-            const uint32_t tmb = c.tmem_base;
-            constexpr uint32_t idesc = make_idesc(64);
-            int w = wi;
-            // An accumulator takes one dependent MMA per ~90 cycles whatever its width, a 128 x 64 x 16 MMA is
-            // 32 cycles of tensor work: two subtiles (two accumulators) are issued interleaved so that the pipe
-            // is not idle between dependent MMAs.
-            for (int kc = 0; kc < sh.kch; ++kc) {
-                for (int sp = 0; sp < sh.ns; sp += 2) {
-                    const int g0 = gst + sp, g1 = g0 + 1;
-                    const int slot0 = g0 & (kAccSlots - 1), slot1 = g1 & (kAccSlots - 1);
-                    if (kc == 0) {
-                        fwait(c.acc_empty(slot0), ((uint32_t)(g0 / kAccSlots) & 1u) ^ 1u, 4, c.oi);
-                        fwait(c.acc_empty(slot1), ((uint32_t)(g1 / kAccSlots) & 1u) ^ 1u, 4, c.oi);
-                        tc_fence_after();
-                    }
-                    const uint32_t tm_acc0 = tmb + kTmAcc + (uint32_t)(slot0 * 64);
-                    const uint32_t tm_acc1 = tmb + kTmAcc + (uint32_t)(slot1 * 64);
-                    for (int kb = 0; kb < 4; ++kb, w += 2) {
-                        const int s0 = w % kWStages, s1 = (w + 1) % kWStages;
-                        const uint32_t ph0 = (uint32_t)(w / kWStages) & 1u, ph1 = (uint32_t)((w + 1) / kWStages) & 1u;
-                        if (sp == 0) fwait(c.a_full(kb), (uint32_t)(ga + kc) & 1u, 5, c.oi);
-                        if (d2 && kc == 0 && sp == 0 && kb == 0) d2[7] = clock64();      // MMA: A k-block 0 ready
-                        fwait(c.w_full(s0), ph0, 6, c.oi);
-                        fwait(c.w_full(s1), ph1, 6, c.oi);
-                        tc_fence_after();
-                        if (d2 && kc == 0 && sp == 0 && kb == 0) d2[8] = clock64();      // MMA: first W stages ready
-#pragma unroll
-                        for (int k = 0; k < kBK / kUmmaK; ++k) {
-                            const uint32_t koff = (uint32_t)k * kUmmaK * 2;
-                            const uint32_t ah = tmb + (uint32_t)(kb * 32 + k * 8), al = ah + kTmALo;
-                            const uint64_t wh0 = make_desc(c.w_hi(s0) + koff), wl0 = make_desc(c.w_lo(s0) + koff);
-                            const uint64_t wh1 = make_desc(c.w_hi(s1) + koff), wl1 = make_desc(c.w_lo(s1) + koff);
-                            const uint32_t first = (kc | kb | k) ? 1u : 0u;
-                            umma_bf16_ta(tm_acc0, al, wh0, idesc, first);      // small terms first
-                            umma_bf16_ta(tm_acc1, al, wh1, idesc, first);
-                            umma_bf16_ta(tm_acc0, ah, wl0, idesc, 1u);
-                            umma_bf16_ta(tm_acc1, ah, wl1, idesc, 1u);
-                            umma_bf16_ta(tm_acc0, ah, wh0, idesc, 1u);
-                            umma_bf16_ta(tm_acc1, ah, wh1, idesc, 1u);
-                        }
-                        umma_commit(c.w_empty(s0));
-                        umma_commit(c.w_empty(s1));
-                    }
-                    if (kc == sh.kch - 1) {
-                        umma_commit(c.acc_full(slot0));
-                        umma_commit(c.acc_full(slot1));
-                    }
-                }
-                umma_commit(c.a_empty());
-            }
-            if (d2) d2[9] = clock64();             // MMA: last issue
+            if (group_size(sh.ns) == 3) mma_gemm<3>(c, sh, gst, ga, wi, d2);
+            else mma_gemm<2>(c, sh, gst, ga, wi, d2);
         }
         if (sh.kind == FOP_ATTN && elect_one()) attention_mma(c, na);
         if (sh.kind == FOP_ATTN) na += att_rounds(c);
