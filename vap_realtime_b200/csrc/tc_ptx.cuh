@@ -41,14 +41,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a mis-programmed pipeline must fail loudly (trap -> launch failure), never hang the GPU.
+// The loop counts polls instead of reading the clock (CS2R shares the XU pipe with the bf16 conversions of the
+// producer warps) and the failure path is a noreturn call, so nothing is live across the printf.
+static __device__ __noinline__ __attribute__((noreturn)) void mbar_wait_fail() {
+    printf("vapb gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+    __trap();
+    for (;;) {}
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("vapb gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-            __trap();
-        }
+        if (++polls > 40000000u) mbar_wait_fail();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
