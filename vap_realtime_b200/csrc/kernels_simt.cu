@@ -447,7 +447,7 @@ void launch_lstm_cell(const float* G, float* hW, float* cW, float* Y, int n_rows
 // are exchanged through distributed shared memory (st to the 8 peers) + one cluster barrier.
 // Also replaces the gather/scatter of the per-stream (h, c) state.
 // -----------------------------------------------------------------------------------------
-constexpr int kLstmWPitch = 129;
+constexpr int kLstmWPitch = 128;      // W_hh slice as float4 [k / 4][128 gate columns]: one 128-bit conflict-free read per 4 k
 constexpr int kLstmGPitch = 132;
 template <int RT>
 constexpr size_t lstm_smem() { return (size_t)(256 * kLstmWPitch + 2 * RT * kD + RT * kLstmGPitch + RT * 32) * sizeof(float); }
@@ -461,7 +461,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
                  int NC, int n_steps) {
     pdl_trigger();
     extern __shared__ float lsm[];
-    float* sW = lsm;                                   // [256 k][129]  (col = gate*32 + unit)
+    float* sW = lsm;                                   // float4 [64 k-quads][128]  (col = gate*32 + unit)
     float* sH = sW + 256 * kLstmWPitch;                // [2][RT][256]
     float* sG = sH + 2 * kLstmRT * kD;                 // [RT][132]
     float* sC = sG + kLstmRT * kLstmGPitch;            // [RT][32]
@@ -476,20 +476,13 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * 256 + tid;              // (col, k-quad); consecutive lanes -> consecutive k
-            const int col = idx >> 6, kq = idx & 63;
+            const int idx = base + u * 256 + tid;              // (k-quad, col); consecutive lanes -> consecutive columns
+            const int col = idx & 127, kq = idx >> 7;
             const int grow = (col >> 5) * kD + 32 * (int)crank + (col & 31);
             v[u] = __ldg(reinterpret_cast<const float4*>(Whh + (size_t)grow * kD) + kq);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * 256 + tid;
-            const int col = idx >> 6, k = (idx & 63) * 4;
-            sW[(k + 0) * kLstmWPitch + col] = v[u].x;
-            sW[(k + 1) * kLstmWPitch + col] = v[u].y;
-            sW[(k + 2) * kLstmWPitch + col] = v[u].z;
-            sW[(k + 3) * kLstmWPitch + col] = v[u].w;
-        }
+        for (int u = 0; u < 8; ++u) reinterpret_cast<float4*>(sW)[base + u * 256 + tid] = v[u];
     }
     pdl_wait();       // the weights above are constants; everything below depends on earlier kernels
     // initial h (all 256 units of the tile's rows) and c (own 32 units)
@@ -532,8 +525,8 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
         for (int r = 0; r < RH; ++r) acc[r] = 0.f;
 #pragma unroll 4
         for (int k = 0; k < kD; k += 4) {
-            const float w0 = sW[(k + 0) * kLstmWPitch + col], w1 = sW[(k + 1) * kLstmWPitch + col];
-            const float w2 = sW[(k + 2) * kLstmWPitch + col], w3 = sW[(k + 3) * kLstmWPitch + col];
+            const float4 w4 = reinterpret_cast<const float4*>(sW)[(k >> 2) * 128 + col];
+            const float w0 = w4.x, w1 = w4.y, w2 = w4.z, w3 = w4.w;
 #pragma unroll
             for (int r = 0; r < RH; ++r) {
                 const float4 hv = *reinterpret_cast<const float4*>(hcur + (rhalf * RH + r) * kD + k);
@@ -964,14 +957,23 @@ __global__ void __launch_bounds__(128) k_attention_last(AttnArgs a) {
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     float o0 = 0.f, o1 = 0.f;
+    const float* vbase = a.V + (size_t)kvn * T * a.ldv + h * 64 + lane;
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-        const int jend = min(32, t - 32 * jj);
-        for (int l = 0; l < jend; ++l) {
-            const float pj = __shfl_sync(0xffffffffu, s[jj], l) * inv;
-            const float* vr = a.V + ((size_t)kvn * T + (32 * jj + l)) * a.ldv + h * 64;
-            o0 = fmaf(pj, vr[lane], o0);
-            o1 = fmaf(pj, vr[lane + 32], o1);
+        for (int l0 = 0; l0 < 32 && 32 * jj + l0 < t; l0 += 8) {      // 8 keys per pass: all 16 V loads in flight first
+            float va[8], vb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float* vr = vbase + (size_t)min(32 * jj + l0 + u, t - 1) * a.ldv;
+                va[u] = vr[0];
+                vb[u] = vr[32];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float pj = __shfl_sync(0xffffffffu, s[jj], l0 + u) * inv;      // 0 for keys >= t
+                o0 = fmaf(pj, va[u], o0);
+                o1 = fmaf(pj, vb[u], o1);
+            }
         }
     }
     float* orow = a.O + (size_t)n * a.ldo + h * 64;
@@ -1017,12 +1019,13 @@ void launch_vad(const float* X, const int* tvalid, const float* w, const float* 
 // -----------------------------------------------------------------------------------------
 constexpr int kHeadWarps = 16;
 
-// four dot products of 256-wide weight rows with a vector in smem; all weight loads issued up front
-__device__ __forceinline__ void warp_dot256_x4(const float* __restrict__ W, int o0, int n_rows, const float* sx, int lane,
-                                               float (&y)[4]) {
-    float ww[4][8];
+// NQ dot products of 256-wide weight rows with a vector in smem; all weight loads issued up front
+template <int NQ>
+__device__ __forceinline__ void warp_dot256(const float* __restrict__ W, int o0, int n_rows, const float* sx, int lane,
+                                            float (&y)[NQ]) {
+    float ww[NQ][8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
         const int o = min(o0 + q, n_rows - 1);
         load_row8(W + (size_t)o * kD, lane, ww[q]);
     }
@@ -1033,7 +1036,7 @@ __device__ __forceinline__ void warp_dot256_x4(const float* __restrict__ W, int 
         xx[4 + i] = sx[128 + lane * 4 + i];
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s = fmaf(ww[q][i], xx[i], s);
@@ -1042,7 +1045,7 @@ __device__ __forceinline__ void warp_dot256_x4(const float* __restrict__ W, int 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) y[q] += __shfl_xor_sync(0xffffffffu, y[q], o);
+        for (int q = 0; q < NQ; ++q) y[q] += __shfl_xor_sync(0xffffffffu, y[q], o);
     }
 }
 
@@ -1064,13 +1067,14 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_head(HeadArgs a) {
         sx[1][tid] = a.X[r1 * kD + tid];
     }
     __syncthreads();
-    for (int o0 = warp * 4; o0 < kD; o0 += kHeadWarps * 4) {
-        float ya[4], yb[4];
-        warp_dot256_x4(a.Wa, o0, kD, sx[0], lane, ya);
-        warp_dot256_x4(a.Wb, o0, kD, sx[1], lane, yb);
+    // 16 warps x 8 rows x 2 matrices: each warp has its 16 weight rows of a pass in flight together, two passes
+    for (int o0 = warp * 8; o0 < kD; o0 += kHeadWarps * 8) {
+        float ya[8], yb[8];
+        warp_dot256<8>(a.Wa, o0, kD, sx[0], lane, ya);
+        warp_dot256<8>(a.Wb, o0, kD, sx[1], lane, yb);
         if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
                 sy[0][o0 + q] = ya[q];
                 sy[1][o0 + q] = yb[q];
             }
@@ -1097,12 +1101,12 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_head(HeadArgs a) {
         if (a.comb_tap) a.comb_tap[(size_t)b * kD + tid] = sh[tid];
     }
     __syncthreads();
-    for (int o0 = warp * 4; o0 < a.n_out; o0 += kHeadWarps * 4) {
-        float y[4];
-        warp_dot256_x4(a.Wh, o0, a.n_out, sh, lane, y);
+    for (int o0 = warp * 8; o0 < a.n_out; o0 += kHeadWarps * 8) {
+        float y[8];
+        warp_dot256<8>(a.Wh, o0, a.n_out, sh, lane, y);
         if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 8; ++q)
                 if (o0 + q < a.n_out) sl[o0 + q] = y[q] + a.bh[o0 + q];
         }
     }
