@@ -224,22 +224,26 @@ __global__ void __launch_bounds__(256) k_sgemm64(GemmArgs g) {
     const float* aptr = (am < g.M) ? (g.A + rowmap_off(g.amap, am) + kq) : nullptr;
     const float* wptr = g.W + (size_t)(n0 + lr) * g.K + kq;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 ra0, ra1, rw0, rw1;
-    auto gload = [&](int kt) {
+    // register prefetch two k-tiles ahead (an L2 / HBM round trip is longer than one tile of FMAs), smem double buffer
+    struct Regs { float4 a0, a1, w0, w1; };
+    auto gload = [&](int kt, Regs& r) {
         const size_t o = (size_t)kt * SK_;
-        ra0 = aptr ? __ldg(reinterpret_cast<const float4*>(aptr + o)) : z4;
-        ra1 = aptr ? __ldg(reinterpret_cast<const float4*>(aptr + o + 16)) : z4;
-        rw0 = __ldg(reinterpret_cast<const float4*>(wptr + o));
-        rw1 = __ldg(reinterpret_cast<const float4*>(wptr + o + 16));
+        r.a0 = aptr ? __ldg(reinterpret_cast<const float4*>(aptr + o)) : z4;
+        r.a1 = aptr ? __ldg(reinterpret_cast<const float4*>(aptr + o + 16)) : z4;
+        r.w0 = __ldg(reinterpret_cast<const float4*>(wptr + o));
+        r.w1 = __ldg(reinterpret_cast<const float4*>(wptr + o + 16));
     };
-    auto sstore = [&](int buf) {
-        As[buf][kq + 0][lr] = ra0.x; As[buf][kq + 1][lr] = ra0.y; As[buf][kq + 2][lr] = ra0.z; As[buf][kq + 3][lr] = ra0.w;
-        As[buf][kq + 16][lr] = ra1.x; As[buf][kq + 17][lr] = ra1.y; As[buf][kq + 18][lr] = ra1.z; As[buf][kq + 19][lr] = ra1.w;
-        Bs[buf][kq + 0][lr] = rw0.x; Bs[buf][kq + 1][lr] = rw0.y; Bs[buf][kq + 2][lr] = rw0.z; Bs[buf][kq + 3][lr] = rw0.w;
-        Bs[buf][kq + 16][lr] = rw1.x; Bs[buf][kq + 17][lr] = rw1.y; Bs[buf][kq + 18][lr] = rw1.z; Bs[buf][kq + 19][lr] = rw1.w;
+    auto sstore = [&](int buf, const Regs& r) {
+        As[buf][kq + 0][lr] = r.a0.x; As[buf][kq + 1][lr] = r.a0.y; As[buf][kq + 2][lr] = r.a0.z; As[buf][kq + 3][lr] = r.a0.w;
+        As[buf][kq + 16][lr] = r.a1.x; As[buf][kq + 17][lr] = r.a1.y; As[buf][kq + 18][lr] = r.a1.z; As[buf][kq + 19][lr] = r.a1.w;
+        Bs[buf][kq + 0][lr] = r.w0.x; Bs[buf][kq + 1][lr] = r.w0.y; Bs[buf][kq + 2][lr] = r.w0.z; Bs[buf][kq + 3][lr] = r.w0.w;
+        Bs[buf][kq + 16][lr] = r.w1.x; Bs[buf][kq + 17][lr] = r.w1.y; Bs[buf][kq + 18][lr] = r.w1.z; Bs[buf][kq + 19][lr] = r.w1.w;
     };
-    gload(0);
-    sstore(0);
+    const int nk = g.K / SK_;
+    Regs r0, r1;
+    gload(0, r0);
+    if (nk > 1) gload(1, r1);
+    sstore(0, r0);
     __syncthreads();
     const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, 4 x 4 outputs each
     float acc[4][4];
@@ -247,10 +251,7 @@ __global__ void __launch_bounds__(256) k_sgemm64(GemmArgs g) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int nk = g.K / SK_;
-    for (int kt = 0; kt < nk; ++kt) {
-        const int cur = kt & 1;
-        if (kt + 1 < nk) gload(kt + 1);
+    auto compute = [&](int cur) {
 #pragma unroll
         for (int k = 0; k < SK_; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
@@ -261,8 +262,19 @@ __global__ void __launch_bounds__(256) k_sgemm64(GemmArgs g) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
-        if (kt + 1 < nk) sstore(cur ^ 1);
+    };
+    // two k-tiles per trip so that the register sets keep their names (r1 holds tile kt + 1, r0 gets tile kt + 2, ...)
+    for (int kt = 0; kt < nk; kt += 2) {
+        if (kt + 2 < nk) gload(kt + 2, r0);
+        compute(0);
+        if (kt + 1 < nk) sstore(1, r1);
         __syncthreads();
+        if (kt + 1 < nk) {
+            if (kt + 3 < nk) gload(kt + 3, r1);
+            compute(1);
+            if (kt + 2 < nk) sstore(0, r0);
+            __syncthreads();
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
