@@ -275,3 +275,36 @@ def test_full_size_batch_invariance(vap_weights, T, B):
     print(f"T={T} B={B}: batch invariance {worst_inv:.2e}, vs oracle {worst_or:.2e}")
     assert worst_inv < 1e-6
     assert worst_or < 1e-4
+
+
+@pytest.mark.parametrize("T", [3, 33, 64, 65, 100, 128])
+def test_stream_kernel_window_edges(T):
+    """Per-stream persistent transformer kernel at the edges of its two tilings: 2T <= 128 rows per cluster
+    (both channels in one M tile, N split over the two CTAs) up to T = 64, one channel per CTA from T = 65 to
+    the maximum window of 128 frames.  Random weights, non-identity slots, warm-up (t < T) and sliding window;
+    checked against the oracle and against the batched per-op kernels ("fused" = 0)."""
+    w = weights.random_tensors(seed=5)
+    n_steps = T + 5 if T < 100 else T + 3
+    oracle = VapOracle(w, 20, T, "vap")
+    fused = VapEngine(w, 20, T, max_streams=8, max_batch=3)
+    plain = VapEngine(w, 20, T, max_streams=8, max_batch=3)
+    for e in (fused, plain):
+        e.set_option("gemm", 1)
+    fused.set_option("fused", 2)          # always (also the default here: 2B <= 148)
+    plain.set_option("fused", 0)
+    slots = [6, 0, 3]
+    audio = np.stack([synthetic_audio(20 + s, n_steps) for s in range(3)])
+    st = OracleState(3)
+    worst_or, worst_ab = 0.0, 0.0
+    for n in range(n_steps):
+        a = np.ascontiguousarray(chunk(audio, n))
+        x = fused.step(torch.from_numpy(a).cuda(), slots).cpu().numpy()
+        y = plain.step(torch.from_numpy(a).cuda(), slots).cpu().numpy()
+        want = oracle.step(a, st).numpy()
+        assert np.isfinite(x).all()
+        worst_or = max(worst_or, np.abs(x - want).max())
+        worst_ab = max(worst_ab, np.abs(x - y).max())
+    print(f"stream kernel T={T}: vs oracle {worst_or:.2e}, vs batched kernels {worst_ab:.2e}, {fused.last_launch_count} / {plain.last_launch_count} kernels")
+    assert fused.last_launch_count < plain.last_launch_count
+    assert worst_or < 1e-4
+    assert worst_ab < 5e-5

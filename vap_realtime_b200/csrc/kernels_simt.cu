@@ -515,7 +515,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 
     constexpr int RH = kLstmRT / 2;                     // rows per thread in the GEMV phase
-    constexpr int RC = kLstmRT / 8;                     // rows per thread in the cell phase
+    constexpr int RC = (kLstmRT + 7) / 8;               // rows per thread in the cell phase (rows cr + 8 * rr < RT)
     const int col = tid & 127, rhalf = tid >> 7;       // thread -> one gate column, half of the rows
     const int gcol = (col >> 5) * kD + 32 * (int)crank + (col & 31);
     const int cu = tid & 31, cr = tid >> 5;            // cell phase: unit cu, rows cr + 8 * rr
@@ -556,6 +556,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
 #pragma unroll
         for (int rr = 0; rr < RC; ++rr) {
             const int r = cr + 8 * rr;
+            if (r >= kLstmRT) continue;
             const float* gr = sG + r * kLstmGPitch;
             const float gi = gr[cu], gf = gr[32 + cu], gg = gr[64 + cu], go = gr[96 + cu];
             const float c = sigmoidf_(gf) * sC[r * 32 + cu] + sigmoidf_(gi) * tanhf(gg);
@@ -580,7 +581,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
 #pragma unroll
     for (int rr = 0; rr < RC; ++rr) {
         const int r = cr + 8 * rr, n = row0 + r;
-        if (n < NC) {
+        if (r < kLstmRT && n < NC) {
             const size_t o = ((size_t)ids[n >> 1] * 2 + (n & 1)) * kD + 32 * crank + cu;
             hS[o] = h_last[rr];
             cS[o] = sC[r * 32 + cu];
@@ -588,24 +589,55 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
     }
 }
 
+template <int RT>
+static int lstm_max_clusters() {          // co-resident clusters of 8 CTAs on this device (GPCs with < 16 free SMs hold one, not two)
+    cudaFuncSetAttribute(k_lstm_recurrent<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<RT>());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(8 * 32);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = lstm_smem<RT>();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_lstm_recurrent<RT>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = 8;
+    }
+    return n;
+}
+
 void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* cS, const int* ids, float* Y, int NC,
                            int n_steps, cudaStream_t st) {
+    // Row tile = the smallest of {8, 10, 12, 16} rows whose clusters all fit ONE wave: a second wave doubles the
+    // kernel, and 16 clusters of 8 CTAs do not fit every B200 (15 on the dies measured: 128 chunks -> 10-row tiles,
+    // 13 clusters on 104 SMs instead of 8 clusters on 64).  Above 16 rows per resident cluster: 16-row tiles, several waves.
     static OncePerDevice once;
+    static int max_cl[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
     if (once.first()) {
-        cudaFuncSetAttribute(k_lstm_recurrent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<8>());
-        cudaFuncSetAttribute(k_lstm_recurrent<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem<16>());
+        const int a = lstm_max_clusters<8>(), b = lstm_max_clusters<10>(), c = lstm_max_clusters<12>(), d = lstm_max_clusters<16>();
+        max_cl[dev] = a < b ? a : b;
+        max_cl[dev] = max_cl[dev] < c ? max_cl[dev] : c;
+        max_cl[dev] = max_cl[dev] < d ? max_cl[dev] : d;
     }
-    // 8-row tiles only for small batches: 16 clusters of 8 CTAs do not fit one wave on every B200 (GPCs with fewer
-    // than 16 free SMs take one cluster, not two), and a second wave doubles the kernel (measured: 16-row tiles
-    // are 22 us faster at NC = 128, profiles/r01_m_lstm_tiles.log)
     static const int force_rt = getenv("VAPB_LSTM_RT") ? atoi(getenv("VAPB_LSTM_RT")) : 0;      // experiment knob
-    if (force_rt != 16 && (force_rt == 8 || NC <= 64)) {
-        const int tiles = (NC + 7) / 8;
-        launch_k(k_lstm_recurrent<8>, dim3(tiles * 8), dim3(256), lstm_smem<8>(), st, Gx, Whh, hS, cS, ids, Y, NC, n_steps);
-    } else {
-        const int tiles = (NC + 15) / 16;
-        launch_k(k_lstm_recurrent<16>, dim3(tiles * 8), dim3(256), lstm_smem<16>(), st, Gx, Whh, hS, cS, ids, Y, NC, n_steps);
-    }
+    int rt = 16;
+    const int cands[4] = {8, 10, 12, 16};
+    for (int i = 3; i >= 0; --i)
+        if ((NC + cands[i] - 1) / cands[i] <= max_cl[dev]) rt = cands[i];
+    if (force_rt) rt = force_rt;
+#define VAPB_LSTM_LAUNCH(RT_)                                                                                              \
+    launch_k(k_lstm_recurrent<RT_>, dim3(((NC + RT_ - 1) / RT_) * 8), dim3(256), lstm_smem<RT_>(), st, Gx, Whh, hS, cS, ids, Y, NC, n_steps)
+    if (rt == 8) VAPB_LSTM_LAUNCH(8);
+    else if (rt == 10) VAPB_LSTM_LAUNCH(10);
+    else if (rt == 12) VAPB_LSTM_LAUNCH(12);
+    else VAPB_LSTM_LAUNCH(16);
+#undef VAPB_LSTM_LAUNCH
 }
 
 // -----------------------------------------------------------------------------------------
