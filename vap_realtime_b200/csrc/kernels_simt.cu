@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_sgemm(GemmArgs g) {
 constexpr int SM_ = 64, SN_ = 64, SK_ = 32, SLD = 68;
 
 __global__ void __launch_bounds__(256) k_sgemm64(GemmArgs g) {
-    pdl_trigger();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // lets the LSTM kernel behind it start its weight fill early (no-op otherwise)
     pdl_wait();
     __shared__ __align__(16) float As[2][SK_][SLD];
     __shared__ __align__(16) float Bs[2][SK_][SLD];
@@ -496,7 +496,8 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
 #pragma unroll
         for (int u = 0; u < 8; ++u) reinterpret_cast<float4*>(sW)[base + u * 256 + tid] = v[u];
     }
-    pdl_wait();       // the weights above are constants; everything below depends on earlier kernels
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // programmatic dependent launch: the weight fill above overlaps the
+                                                            // input-projection GEMM in front of this kernel; everything below depends on it
     // initial h (all 256 units of the tile's rows) and c (own 32 units)
     for (int i = tid; i < kLstmRT * kD; i += 256) {
         const int r = i >> 8, k = i & 255, n = row0 + r;
@@ -631,8 +632,21 @@ void launch_lstm_recurrent(const float* Gx, const float* Whh, float* hS, float* 
     for (int i = 3; i >= 0; --i)
         if ((NC + cands[i] - 1) / cands[i] <= max_cl[dev]) rt = cands[i];
     if (force_rt) rt = force_rt;
-#define VAPB_LSTM_LAUNCH(RT_)                                                                                              \
-    launch_k(k_lstm_recurrent<RT_>, dim3(((NC + RT_ - 1) / RT_) * 8), dim3(256), lstm_smem<RT_>(), st, Gx, Whh, hS, cS, ids, Y, NC, n_steps)
+    static const int use_pdl = getenv("VAPB_LSTM_PDL") ? atoi(getenv("VAPB_LSTM_PDL")) : 1;     // experiment knob
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+#define VAPB_LSTM_LAUNCH(RT_)                                                                        \
+    do {                                                                                             \
+        cfg.gridDim = dim3(((NC + RT_ - 1) / RT_) * 8);                                              \
+        cfg.dynamicSmemBytes = lstm_smem<RT_>();                                                     \
+        cudaLaunchKernelEx(&cfg, k_lstm_recurrent<RT_>, Gx, Whh, hS, cS, ids, Y, NC, n_steps);        \
+    } while (0)
     if (rt == 8) VAPB_LSTM_LAUNCH(8);
     else if (rt == 10) VAPB_LSTM_LAUNCH(10);
     else if (rt == 12) VAPB_LSTM_LAUNCH(12);
