@@ -24,8 +24,7 @@ for l in range(3):
     names += [f"L{l}.ln_qkv", f"L{l}.attn", f"L{l}.proj"]
     if l > 0: names += [f"L{l}.ln_q_cross", f"L{l}.attn_cross", f"L{l}.proj_c"]
     names += [f"L{l}.ln_ffn1", f"L{l}.ffn2"]
-    if l == 0: names.append("vad")
-names += ["L3.kv_cross", "L3.ln_kv_self", "gather_last"]
+names += ["L3.kv_cross", "L3.ln_kv_self"]
 for n, c in zip(names, clk):
     print(f"{n:16s} {c:9.0f} cyc  {c / 1965.0:7.2f} us")
 fine = clk[len(names):]

@@ -14,6 +14,7 @@
 #include "fused_tf.cuh"
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
 #include <string>
 
 namespace vapb {
@@ -599,6 +600,9 @@ __device__ __forceinline__ long long* fine_stamps(const FusedParams& p, int oi) 
 __device__ __forceinline__ void workers_loop(Ctx& c, const FusedParams& p, int id, int cnt) {
     int gst = 0, ga = 0, na = 0;     // running counters: accumulator subtiles, A generations, attention rounds
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && c.tid == 0;
+    // programmatic dependent launch: set-up and the first weight tiles overlap the tail of the kernel in front; the
+    // workers are the only warps that read what it produced (the ring)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int oi = 0; oi < p.n_ops; ++oi) {
         const FOpFields& op = c.opslot[oi & 1];      // copied one op ahead by the MMA warp, visible through the cluster barrier
         c.oi = oi;
@@ -619,37 +623,27 @@ __device__ __forceinline__ void workers_loop(Ctx& c, const FusedParams& p, int i
             const int ch = c.r;
             const float* rg = p.ring + ((size_t)id * 2 + ch) * p.T * kD;
             float* xo = p.X + (size_t)(2 * c.b + ch) * p.T * kD;
-            for (int i = c.tid; i < p.T * 64; i += kWorkers * 32) {
-                const int j = i >> 6, q = i & 63;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < c.t) {
-                    const int slot = (cnt - c.t + j) % p.T;
-                    v = ldcg4(rg + (size_t)slot * kD + 4 * q);
+            // thread = (row j0 + 4 u, float4 q): 8 rows per pass with all loads in flight (a plain loop pays one L2 round
+            // trip per row)
+            const int q4 = c.tid & 63, j0 = c.tid >> 6;
+            for (int jb = 0; jb < p.T; jb += 32) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = jb + j0 + 4 * u;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < c.t) {
+                        const int slot = (cnt - c.t + j) % p.T;
+                        v[u] = ldcg4(rg + (size_t)slot * kD + 4 * q4);
+                    }
                 }
-                *reinterpret_cast<float4*>(xo + (size_t)j * kD + 4 * q) = v;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = jb + j0 + 4 * u;
+                    if (j < p.T) *reinterpret_cast<float4*>(xo + (size_t)j * kD + 4 * q4) = v[u];
+                }
             }
             if (c.r == 0 && c.tid == 0) p.tvalid[c.b] = c.t;
-        } else if (sh.kind == FOP_VAD) {
-            // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
-            if (c.warp == 0) {
-                const float* xr = p.X + ((size_t)(2 * c.b + c.r) * p.T + (c.t - 1)) * kD + 8 * c.lane;
-                const float4 x0 = ldcg4(xr), x1 = ldcg4(xr + 4);
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane + 4));
-                float s = 0.f;
-                s = fmaf(x0.x, w0.x, s); s = fmaf(x0.y, w0.y, s); s = fmaf(x0.z, w0.z, s); s = fmaf(x0.w, w0.w, s);
-                s = fmaf(x1.x, w1.x, s); s = fmaf(x1.y, w1.y, s); s = fmaf(x1.z, w1.z, s); s = fmaf(x1.w, w1.w, s);
-                s = warp_sum_f(s) + __ldg(p.va_b);
-                if (c.lane == 0) p.out[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
-            }
-        } else if (sh.kind == FOP_GATHER_LAST) {
-            if (c.warp == 0) {
-                const int n = 2 * c.b + c.r;
-                const float* xr = p.X + ((size_t)n * p.T + (c.t - 1)) * kD + 8 * c.lane;
-                float* xo = p.Xl + (size_t)n * kD + 8 * c.lane;
-                *reinterpret_cast<float4*>(xo) = ldcg4(xr);
-                *reinterpret_cast<float4*>(xo + 4) = ldcg4(xr + 4);
-            }
         }
         cl_arrive();
         cl_wait();
@@ -843,7 +837,30 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
         if (c.warp == kWorkers) tma_loop(c, p);
         else if (c.warp == kWorkers + 1) mma_loop(c, p);
         else {
-            for (int oi = 0; oi < p.n_ops; ++oi) {   // two spare warps complete the third warpgroup
+            // two spare warps complete the third warpgroup; the first one runs the small side tasks next to the op that
+            // allows it (they only read X, which that op does not modify), so they cost no cluster barrier of their own
+            for (int oi = 0; oi < p.n_ops; ++oi) {
+                const int side = c.warp == kWorkers + 2 ? __ldg(&p.ops[oi].f.side) : 0;
+                if (side == FSIDE_VAD) {
+                    // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
+                    const float* xr = p.X + ((size_t)(2 * c.b + c.r) * p.T + (c.t - 1)) * kD + 8 * c.lane;
+                    const float4 x0 = ldcg4(xr), x1 = ldcg4(xr + 4);
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane));
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane + 4));
+                    float s = 0.f;
+                    s = fmaf(x0.x, w0.x, s); s = fmaf(x0.y, w0.y, s); s = fmaf(x0.z, w0.z, s); s = fmaf(x0.w, w0.w, s);
+                    s = fmaf(x1.x, w1.x, s); s = fmaf(x1.y, w1.y, s); s = fmaf(x1.z, w1.z, s); s = fmaf(x1.w, w1.w, s);
+                    s = warp_sum_f(s) + __ldg(p.va_b);
+                    if (c.lane == 0) p.out[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
+                } else if (side == FSIDE_GATHER_LAST) {
+                    // newest frame of channel r -> one row per sequence for the pruned layer's tail
+                    const int n = 2 * c.b + c.r;
+                    const float* xr = p.X + ((size_t)n * p.T + (c.t - 1)) * kD + 8 * c.lane;
+                    float* xo = p.Xl + (size_t)n * kD + 8 * c.lane;
+                    *reinterpret_cast<float4*>(xo) = ldcg4(xr);
+                    *reinterpret_cast<float4*>(xo + 4) = ldcg4(xr + 4);
+                }
+                __syncwarp();
                 cl_arrive();
                 cl_wait();
             }
@@ -870,7 +887,20 @@ bool fused_prepare(std::string& err) {
 }
 
 cudaError_t launch_fused_tf(const FusedParams& p, int B, cudaStream_t st) {
-    return launch_k_cluster(k_stream_tf, dim3(2 * B), dim3(kThreadsF), kSmemF, st, 2, p);
+    static const int use_pdl = getenv("VAPB_STREAM_PDL") ? atoi(getenv("VAPB_STREAM_PDL")) : 0;     // measured 3.5 us SLOWER than a plain graph edge (636.2 vs 632.6 us per step): off
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * B);
+    cfg.blockDim = dim3(kThreadsF);
+    cfg.dynamicSmemBytes = kSmemF;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, k_stream_tf, p);
 }
 
 }  // namespace vapb

@@ -16,7 +16,8 @@
 
 namespace vapb {
 
-enum FOpKind { FOP_GEMM = 0, FOP_ATTN = 1, FOP_GATHER_RING = 2, FOP_VAD = 3, FOP_GATHER_LAST = 4 };
+enum FOpKind { FOP_GEMM = 0, FOP_ATTN = 1, FOP_GATHER_RING = 2 };
+enum FSide { FSIDE_NONE = 0, FSIDE_VAD = 1, FSIDE_GATHER_LAST = 2 };
 
 struct FOpFields {                   // 128 bytes: copied to shared memory one op ahead
     int kind;
@@ -24,7 +25,7 @@ struct FOpFields {                   // 128 bytes: copied to shared memory one o
     int K, N, act, lda, ldc;
     // attention
     int sibling, ldq, ldk, ldv, ldo;
-    int pad_;
+    int side;            // side task of the spare warp during this op: 0 none, 1 vad of the ar_channel output, 2 newest-frame gather
     const float* A;
     const float* ln_w;
     const float* ln_b;

@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(256) k_ln_gelu_ring(const float* __restrict__ 
                                                       const float* __restrict__ b, float* ring,
                                                       const int* __restrict__ count, const int* __restrict__ ids,
                                                       int T, float* e_out, int nsplit, long long split_stride) {
-    pdl_trigger();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the stream kernel behind it sets up (TMEM, barriers, first W tiles) early
     pdl_wait();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (n >= 2 * B) return;

@@ -486,6 +486,7 @@ int build_fused_ops(vapb_ctx* c) {
     ops.push_back(fop_misc(FOP_GATHER_RING));
     for (int l = 0; l < 3; ++l) {
         const LayerWeights& lw = c->layers[l];
+        const size_t first = ops.size();
         if (lw.cross) ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_kv_c, nullptr, nullptr, nullptr, c->KVc, 2 * kD, 2 * kD, 0));
         ops.push_back(fop_gemm(c->X, kD, kD, lw.sa.tc_qkv, lw.ln_sa_w, lw.ln_sa_b, nullptr, c->QKV, 3 * kD, 3 * kD, 0));
         ops.push_back(fop_attn(c->QKV, 3 * kD, c->QKV + kD, 3 * kD, c->QKV + 2 * kD, 3 * kD, c->O, lw.sa.slopes, 0));
@@ -497,13 +498,14 @@ int build_fused_ops(vapb_ctx* c) {
         }
         ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_w1, lw.ln_ff_w, lw.ln_ff_b, nullptr, c->Hd, kFF, kFF, 1));
         ops.push_back(fop_gemm(c->Hd, kFF, kFF, lw.tc_w2, nullptr, nullptr, c->X, c->X, kD, kD, 0));
-        if (l == 0 && c->head_kind == VAPB_HEAD_VAP) ops.push_back(fop_misc(FOP_VAD));
+        // vad reads the ar_channel output: a side task of the first op of cross layer 0 (which only reads X)
+        if (l == 1 && c->head_kind == VAPB_HEAD_VAP) ops[first].f.side = FSIDE_VAD;
     }
     {   // pruned last layer: only its window-wide K / V projections and the newest-frame gather
         const LayerWeights& lw = c->layers[3];
         ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_kv_c, nullptr, nullptr, nullptr, c->KVc, 2 * kD, 2 * kD, 0));
+        ops.back().f.side = FSIDE_GATHER_LAST;
         ops.push_back(fop_gemm(c->X, kD, kD, lw.sa.tc_kv, lw.ln_sa_w, lw.ln_sa_b, nullptr, c->QKV, 2 * kD, 2 * kD, 0));
-        ops.push_back(fop_misc(FOP_GATHER_LAST));
     }
     c->n_fops = (int)ops.size();
     void* d = nullptr;
