@@ -118,6 +118,13 @@ VAPB_API int vapb_import_state(vapb_handle h, int stream_id, const float* state)
  *   "gemm"      0/1   0 = fp32 CUDA-core GEMMs everywhere, 1 = tcgen05 bf16 hi/lo x3
  *                     tensor-core GEMMs for conv1-4, downsample and the transformer
  *   "keep_taps" 0/1   keep intermediates readable through vapb_debug_tensor
+ *   "fused"     0/1/2 transformer stack as ONE per-stream persistent kernel (a cluster of two CTAs per stream):
+ *                     0 = never (batched per-op kernels), 1 = while all clusters are co-resident, i.e. 2B <= 148
+ *                     (default), 2 = always
+ *   "fused_dbg" n     n > 0: clock64 stamps per op of that kernel (fine stamps for op n - 1), read back through
+ *                     vapb_debug_tensor("fused_clocks")
+ *   tuning / ablation switches, each measured in profiles/: "prune", "splitk", "conv4p", "lstm_fused", "fuse_ln",
+ *   "k256", "tile_n", "cluster2", "attn_rk", "fork", "pdl", "timing"
  */
 VAPB_API int vapb_set_option(vapb_handle h, const char* key, int value);
 VAPB_API int vapb_get_option(vapb_handle h, const char* key, int* value);

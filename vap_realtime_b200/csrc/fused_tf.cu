@@ -41,7 +41,6 @@ constexpr uint32_t kTmALo = 128, kTmAcc = 256;
 constexpr int kAccSlots = 4;                          // 4 x 64 accumulator columns
 constexpr int kSmemF = kWStages * 2 * kWTile + kUniBytes + 256 /*barriers*/ + 256 /*two op slots*/ + 1024;
 static_assert(40 + 16 * kWStages + 16 * kAccSlots + 8 + 48 <= 256, "barrier block too small");
-constexpr int kKPitch = 68;                           // attention: K rows in smem (float4 reads, conflict free per quarter warp)
 
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
@@ -53,11 +52,6 @@ __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterp
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 
@@ -106,6 +100,19 @@ struct Ctx {
     __device__ __forceinline__ uint32_t uni_u32() const { return wbase + kWStages * 2 * kWTile; }
 };
 
+// exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, the level of erff itself): one fast
+// reciprocal, one ex2 and five FMAs instead of erff's ~22 instructions; 192 GELUs per thread in an FFN1 epilogue
+__device__ __forceinline__ float gelu_as(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    const float er = 1.0f - pl * t * __expf(-z * z);          // erf(|x| / sqrt 2)
+    return 0.5f * x + 0.5f * fabsf(x) * er;                   // 0.5 x (1 + sign(x) erf(|x| / sqrt 2))
+}
+
 // One 32 x 32 block of the accumulator: TMEM -> registers -> per-warp smem transpose -> (GELU, + R) -> global.
 template <bool HAS_R, bool GELU>
 __device__ __forceinline__ void epi_block(const uint32_t (&raw)[32], float* tbuf, int lane, int rows_valid, const float* Rb,
@@ -131,7 +138,7 @@ __device__ __forceinline__ void epi_block(const uint32_t (&raw)[32], float* tbuf
         const int rr = 4 * it + sub;
         float4 x = *reinterpret_cast<const float4*>(tbuf + rr * kEpiPitch + c4);
         if (GELU) {
-            x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+            x.x = gelu_as(x.x); x.y = gelu_as(x.y); x.z = gelu_as(x.z); x.w = gelu_as(x.w);
         }
         if (HAS_R) {
             x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
@@ -621,18 +628,19 @@ __device__ __forceinline__ void workers_loop(Ctx& c, const FusedParams& p, int i
         } else if (sh.kind == FOP_GATHER_RING) {
             // X rows of channel r = ring rows oldest first, zero rows above t (vap_main.py:274-283)
             const int ch = c.r;
-            const float* rg = p.ring + ((size_t)id * 2 + ch) * p.T * kD;
+            const float* rg = p.ring + ((size_t)id * 2 + ch) * p.T * kD;      // (row layout note: a lane owns 8 consecutive floats below)
             float* xo = p.X + (size_t)(2 * c.b + ch) * p.T * kD;
             // thread = (row j0 + 4 u, float4 q): 8 rows per pass with all loads in flight (a plain loop pays one L2 round
             // trip per row)
             const int q4 = c.tid & 63, j0 = c.tid >> 6;
+            const int jnew = p.ds_part ? c.t - 1 : -1;           // newest frame: produced below, not yet in the ring
             for (int jb = 0; jb < p.T; jb += 32) {
                 float4 v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int j = jb + j0 + 4 * u;
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j < c.t) {
+                    if (j < c.t && j != jnew) {
                         const int slot = (cnt - c.t + j) % p.T;
                         v[u] = ldcg4(rg + (size_t)slot * kD + 4 * q4);
                     }
@@ -640,8 +648,44 @@ __device__ __forceinline__ void workers_loop(Ctx& c, const FusedParams& p, int i
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int j = jb + j0 + 4 * u;
-                    if (j < p.T) *reinterpret_cast<float4*>(xo + (size_t)j * kD + 4 * q4) = v[u];
+                    if (j < p.T && j != jnew) *reinterpret_cast<float4*>(xo + (size_t)j * kD + 4 * q4) = v[u];
                 }
+            }
+            if (p.ds_part && c.warp == kWorkers - 1) {
+                // downsample tail of channel r: sum the split-K partials, LayerNorm (biased variance), exact GELU
+                const int n = 2 * c.b + ch;
+                const float* pr = p.ds_part + (size_t)n * kD + 8 * c.lane;
+                float4 a = ldcg4(pr), b4 = ldcg4(pr + 4);
+                for (int z = 1; z < p.ds_nsplit; ++z) {
+                    const float4 a2 = ldcg4(pr + (size_t)z * p.ds_stride), b2 = ldcg4(pr + (size_t)z * p.ds_stride + 4);
+                    a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b4.x += b2.x; b4.y += b2.y; b4.z += b2.z; b4.w += b2.w;
+                }
+                float v8[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sum += v8[i];
+                const float mean = warp_sum_f(sum) * (1.0f / 256.0f);
+                float sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float d = v8[i] - mean;
+                    sq = fmaf(d, d, sq);
+                }
+                const float rstd = 1.0f / sqrtf(warp_sum_f(sq) * (1.0f / 256.0f) + 1e-5f);
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.ds_lnw + 8 * c.lane)), w1 = __ldg(reinterpret_cast<const float4*>(p.ds_lnw + 8 * c.lane + 4));
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ds_lnb + 8 * c.lane)), g1 = __ldg(reinterpret_cast<const float4*>(p.ds_lnb + 8 * c.lane + 4));
+                const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v8[i] = gelu_erf((v8[i] - mean) * rstd * ww[i] + bb[i]);
+                const float4 o0 = make_float4(v8[0], v8[1], v8[2], v8[3]), o1 = make_float4(v8[4], v8[5], v8[6], v8[7]);
+                float* dst[3] = {p.ring + (((size_t)id * 2 + ch) * p.T + (cnt - 1) % p.T) * kD, xo + (size_t)(c.t - 1) * kD,
+                                 p.e_out ? p.e_out + (size_t)n * kD : nullptr};
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (dst[k]) {
+                        *reinterpret_cast<float4*>(dst[k] + 8 * c.lane) = o0;
+                        *reinterpret_cast<float4*>(dst[k] + 8 * c.lane + 4) = o1;
+                    }
             }
             if (c.r == 0 && c.tid == 0) p.tvalid[c.b] = c.t;
         }

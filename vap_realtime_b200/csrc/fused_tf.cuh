@@ -48,7 +48,16 @@ struct FusedParams {
     int n_ops;
     int T;
     int mode;
-    const float* ring;       // [max_streams][2][T][256]
+    float* ring;             // [max_streams][2][T][256]
+    // downsample tail folded into the ring gather (encoder_components.py:496-511): split-K partials of the downsample
+    // GEMM [ds_nsplit][2B][256] -> sum -> LayerNorm -> GELU -> ring slot count % T (+ X row t-1, + e_out); null = the ring
+    // already holds the newest frame
+    const float* ds_part;
+    long long ds_stride;
+    int ds_nsplit;
+    const float* ds_lnw;
+    const float* ds_lnb;
+    float* e_out;            // [2B][256] tap of the new embedding
     const int* count;
     const int* ids;
     int* tvalid;

@@ -967,7 +967,11 @@ void launch_gather_last(const float* X, const int* tvalid, float* Xl, int n_seq,
     launch_k(k_gather_last, dim3((n_seq + 7) / 8), dim3(256), 0, st, X, tvalid, Xl, n_seq, T);
 }
 
-// one warp per (sequence, head); the query is the newest frame, so every valid key j < t is visible
+// One warp per (sequence, head); the query is the newest frame, so every valid key j < t is visible.
+// Lane = key in BOTH phases (keys lane and lane + 32 of a 64-key group): the K row and then the V row of a lane's keys
+// are fetched with all 32 loads in flight, so a group costs two memory round trips instead of one per 8 keys; the
+// 64 partial output sums of a lane are then reduced across the warp by recursive halving (62 shuffles), which leaves
+// two output dimensions per lane.
 __global__ void __launch_bounds__(128) k_attention_last(AttnArgs a) {
     pdl_trigger();
     pdl_wait();
@@ -983,60 +987,81 @@ __global__ void __launch_bounds__(128) k_attention_last(AttnArgs a) {
         q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
     }
     const float slope = a.slopes[h];
+    const float* kbase = a.K + (size_t)kvn * T * a.ldk + h * 64;
+    const float* vbase = a.V + (size_t)kvn * T * a.ldv + h * 64;
     float s[4];
-    float mx = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-        const int j = lane + 32 * jj;
-        s[jj] = -INFINITY;
-        if (j < t) {
-            const float4* kp = reinterpret_cast<const float4*>(a.K + ((size_t)kvn * T + j) * a.ldk + h * 64);
-            float acc = 0.f;
+    for (int g = 0; g < 2; ++g) {                     // scores of keys lane + 32 * {2g, 2g + 1}
+        s[2 * g] = -INFINITY;
+        s[2 * g + 1] = -INFINITY;
+        if (64 * g < t) {
+            const int ja = lane + 64 * g, jb = ja + 32;
+            const float4* ka = reinterpret_cast<const float4*>(kbase + (size_t)min(ja, t - 1) * a.ldk);
+            const float4* kb = reinterpret_cast<const float4*>(kbase + (size_t)min(jb, t - 1) * a.ldk);
+            float4 ra[16], rb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { ra[i] = ka[i]; rb[i] = kb[i]; }
+            float acca = 0.f, accb = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float4 v = kp[i];
-                acc = fmaf(q[4 * i], v.x, acc);
-                acc = fmaf(q[4 * i + 1], v.y, acc);
-                acc = fmaf(q[4 * i + 2], v.z, acc);
-                acc = fmaf(q[4 * i + 3], v.w, acc);
+                acca = fmaf(q[4 * i], ra[i].x, acca); acca = fmaf(q[4 * i + 1], ra[i].y, acca);
+                acca = fmaf(q[4 * i + 2], ra[i].z, acca); acca = fmaf(q[4 * i + 3], ra[i].w, acca);
+                accb = fmaf(q[4 * i], rb[i].x, accb); accb = fmaf(q[4 * i + 1], rb[i].y, accb);
+                accb = fmaf(q[4 * i + 2], rb[i].z, accb); accb = fmaf(q[4 * i + 3], rb[i].w, accb);
             }
-            s[jj] = acc * 0.0625f + slope * (float)j;
+            if (ja < t) s[2 * g] = acca * 0.0625f + slope * (float)ja;
+            if (jb < t) s[2 * g + 1] = accb * 0.0625f + slope * (float)jb;
         }
-        mx = fmaxf(mx, s[jj]);
     }
+    float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-        const int j = lane + 32 * jj;
-        s[jj] = (j < t) ? expf(s[jj] - mx) : 0.f;
+        s[jj] = (lane + 32 * jj < t) ? expf(s[jj] - mx) : 0.f;
         sum += s[jj];
     }
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
-    float o0 = 0.f, o1 = 0.f;
-    const float* vbase = a.V + (size_t)kvn * T * a.ldv + h * 64 + lane;
+    float o[64];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-        for (int l0 = 0; l0 < 32 && 32 * jj + l0 < t; l0 += 8) {      // 8 keys per pass: all 16 V loads in flight first
-            float va[8], vb[8];
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float* vr = vbase + (size_t)min(32 * jj + l0 + u, t - 1) * a.ldv;
-                va[u] = vr[0];
-                vb[u] = vr[32];
-            }
+    for (int g = 0; g < 2; ++g) {
+        if (64 * g < t) {
+            const int ja = lane + 64 * g, jb = ja + 32;
+            const float4* va = reinterpret_cast<const float4*>(vbase + (size_t)min(ja, t - 1) * a.ldv);
+            const float4* vb = reinterpret_cast<const float4*>(vbase + (size_t)min(jb, t - 1) * a.ldv);
+            float4 ra[16], rb[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float pj = __shfl_sync(0xffffffffu, s[jj], l0 + u) * inv;      // 0 for keys >= t
-                o0 = fmaf(pj, va[u], o0);
-                o1 = fmaf(pj, vb[u], o1);
+            for (int i = 0; i < 16; ++i) { ra[i] = va[i]; rb[i] = vb[i]; }
+            const float pa = s[2 * g] * inv, pb = s[2 * g + 1] * inv;          // 0 for keys >= t
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                o[4 * i] = fmaf(pa, ra[i].x, fmaf(pb, rb[i].x, o[4 * i]));
+                o[4 * i + 1] = fmaf(pa, ra[i].y, fmaf(pb, rb[i].y, o[4 * i + 1]));
+                o[4 * i + 2] = fmaf(pa, ra[i].z, fmaf(pb, rb[i].z, o[4 * i + 2]));
+                o[4 * i + 3] = fmaf(pa, ra[i].w, fmaf(pb, rb[i].w, o[4 * i + 3]));
             }
         }
     }
+    // recursive halving over the warp: after the step with lane-bit `bit` a lane keeps the half of its array selected by
+    // that bit (plus what its partner sent for it); 64 -> 32 -> 16 -> 8 -> 4 -> 2 values
+    int d0 = 0;
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+        const int bit = 16 >> step, half = 32 >> step;
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? o[i] : o[i + half];
+            const float keep = up ? o[i + half] : o[i];
+            o[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+        if (up) d0 += half;
+    }
     float* orow = a.O + (size_t)n * a.ldo + h * 64;
-    orow[lane] = o0;
-    orow[lane + 32] = o1;
+    *reinterpret_cast<float2*>(orow + d0) = make_float2(o[0], o[1]);
 }
 void launch_attention_last(const AttnArgs& a, cudaStream_t st) {
     launch_k(k_attention_last, dim3(a.n_seq), dim3(128), 0, st, a);

@@ -130,26 +130,9 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-// Warp-converged variants: the WHOLE warp executes them with warp-uniform operands and `lead` selects the one
-// issuing lane.  Inside a divergent `if (lane == 0)` the compiler cannot prove the descriptors uniform and wraps
-// every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~90 cycles per MMA, measured).
-__device__ __forceinline__ void umma_bf16_ta_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
-                                               uint32_t lead) {
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.ne.b32 e, %5, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(lead)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t lead) {
-    asm volatile(
-        "{\n\t.reg .pred e;\n\t"
-        "setp.ne.b32 e, %1, 0;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(lead)
-        : "memory");
-}
+// NOTE on issuing tcgen05.mma / TMA from one lane: guard the region with elect_one(), not with `lane == 0`.  Inside a
+// plain divergent branch ptxas cannot prove the descriptors warp-uniform and wraps EVERY tcgen05.mma in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~94 cycles per MMA whatever its width, measured).
 // 32 lanes x 16 columns: thread l of warp w writes v[0..15] to TMEM lane 32 * (w % 4) + l, columns taddr .. taddr + 15
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(

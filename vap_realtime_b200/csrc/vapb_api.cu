@@ -116,6 +116,9 @@ struct vapb_ctx {
     int n_fops = 0;
     long long* fused_clk = nullptr;  // optional clock64 stamps per op (option fused_dbg)
     int opt_fused = 1, opt_fused_dbg = 0;
+    const float* fused_ds_part = nullptr;      // downsample partials handed to the stream kernel (its gather op finishes the embedding)
+    long long fused_ds_stride = 0;
+    int fused_ds_nsplit = 0;
 
     // taps
     std::map<std::string, std::pair<float*, size_t>> taps;
@@ -529,6 +532,8 @@ void fused_transformer(Step& s) {
     p.ops = c->fops; p.n_ops = c->n_fops; p.T = c->T; p.mode = (2 * c->T <= 128) ? 0 : 1;
     p.ring = c->ring; p.count = c->count; p.ids = c->ids_dev; p.tvalid = c->tvalid; p.X = c->X; p.Xl = c->Xl;
     p.va_w = c->va_w; p.va_b = c->va_b; p.out = s.out;
+    p.ds_part = c->fused_ds_part; p.ds_stride = c->fused_ds_stride; p.ds_nsplit = c->fused_ds_nsplit;
+    p.ds_lnw = c->ds_lnw; p.ds_lnb = c->ds_lnb; p.e_out = c->ebuf;
     p.dbg = c->opt_fused_dbg ? c->fused_clk : nullptr;
     p.dbg_op = c->opt_fused_dbg - 1;          // fused_dbg = 1 + index of the op that gets fine stamps
     launch_fused_tf(p, s.B, s.st);
@@ -596,6 +601,10 @@ void enqueue_step(Step& s) {
             launch_scatter_state(c->hS, c->cS, c->ids_dev, c->hW, c->cW, B, st); mark(s, "lstm_state");
         }
     }
+    // one cluster per stream: a win while all clusters are co-resident (2B <= SM count); bigger batches are served
+    // better by the batched per-op kernels, whose GEMM tiles are full (measured B = 128 / 256: r01_n_experiments.md)
+    const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
+    const bool use_stream = c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (2 * B <= 148 || c->opt_fused == 2);
     // ---- downsample conv over exactly n_lstm frames + LayerNorm + GELU -> ring
     {
         const int Kd = c->n_lstm * kD;
@@ -604,17 +613,16 @@ void enqueue_step(Step& s) {
             const long long dstride = (long long)NC * kD;
             gemm(s, "gemm_downsample", c->Y, plain_map(Kd), c->Wds, &c->tc_ds, c->bds, nullptr, plain_map(kD), c->part, plain_map(kD), NC, kD, Kd, 0,
                  nullptr, nullptr, ks, dstride, c->opt_conv4p);
-            launch_ln_gelu_ring(c->part, B, c->ds_lnw, c->ds_lnb, c->ring, c->count, c->ids_dev, T, c->ebuf, st, ks, dstride);
+            if (use_stream) { c->fused_ds_part = c->part; c->fused_ds_stride = dstride; c->fused_ds_nsplit = ks; }
+            else launch_ln_gelu_ring(c->part, B, c->ds_lnw, c->ds_lnb, c->ring, c->count, c->ids_dev, T, c->ebuf, st, ks, dstride);
         } else {
             gemm(s, "gemm_downsample", c->Y, plain_map(Kd), c->Wds, &c->tc_ds, c->bds, nullptr, plain_map(kD), c->dsout, plain_map(kD), NC, kD, Kd, 0);
-            launch_ln_gelu_ring(c->dsout, B, c->ds_lnw, c->ds_lnb, c->ring, c->count, c->ids_dev, T, c->ebuf, st);
+            if (use_stream) { c->fused_ds_part = c->dsout; c->fused_ds_stride = 0; c->fused_ds_nsplit = 1; }
+            else launch_ln_gelu_ring(c->dsout, B, c->ds_lnw, c->ds_lnb, c->ring, c->count, c->ids_dev, T, c->ebuf, st);
         }
-        mark(s, "ln_gelu_ring");
+        if (!use_stream) mark(s, "ln_gelu_ring");      // the stream kernel's gather op finishes the embedding otherwise
     }
-    const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
-    // one cluster per stream: a win while all clusters are co-resident (2B <= SM count); bigger batches are served
-    // better by the batched per-op kernels, whose GEMM tiles are full (measured B = 128 / 256: r01_m_option_ablation.log)
-    if (c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (2 * B <= 148 || c->opt_fused == 2)) {
+    if (use_stream) {
         // ---- ring gather, ar_channel, vad, cross layers 0-1 and the K/V of the pruned last layer: ONE launch,
         //      a cluster of two CTAs per stream (fused_tf.cu); then the newest-frame tail of the last layer
         fused_transformer(s);
