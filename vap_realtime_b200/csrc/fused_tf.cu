@@ -655,10 +655,23 @@ __device__ __forceinline__ void workers_loop(Ctx& c, const FusedParams& p, int i
                 // downsample tail of channel r: sum the split-K partials, LayerNorm (biased variance), exact GELU
                 const int n = 2 * c.b + ch;
                 const float* pr = p.ds_part + (size_t)n * kD + 8 * c.lane;
-                float4 a = ldcg4(pr), b4 = ldcg4(pr + 4);
-                for (int z = 1; z < p.ds_nsplit; ++z) {
-                    const float4 a2 = ldcg4(pr + (size_t)z * p.ds_stride), b2 = ldcg4(pr + (size_t)z * p.ds_stride + 4);
-                    a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b4.x += b2.x; b4.y += b2.y; b4.z += b2.z; b4.w += b2.w;
+                // partial z lives ds_stride floats behind partial z - 1; 8 partials (16 loads) in flight per pass
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+                for (int z0 = 0; z0 < p.ds_nsplit; z0 += 8) {
+                    float4 pa[8], pb[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float* q8 = pr + (size_t)min(z0 + u, p.ds_nsplit - 1) * p.ds_stride;
+                        pa[u] = ldcg4(q8);
+                        pb[u] = ldcg4(q8 + 4);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (z0 + u < p.ds_nsplit) {
+                            a.x += pa[u].x; a.y += pa[u].y; a.z += pa[u].z; a.w += pa[u].w;
+                            b4.x += pb[u].x; b4.y += pb[u].y; b4.z += pb[u].z; b4.w += pb[u].w;
+                        }
+                    }
                 }
                 float v8[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
                 float sum = 0.f;
