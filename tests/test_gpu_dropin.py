@@ -99,3 +99,31 @@ def test_other_frame_rates_random_weights(hz):
         worst = max(worst, np.abs(got - want).max())
     print(f"{hz} Hz: max|d| = {worst:.2e}")
     assert worst < 1e-4
+
+
+def test_stateless_forward_matches_reference_static():
+    """vap_static.VAPRealTimeStatic.forward (the function the reference's ONNX / TFLite exporters trace,
+    tools/vap_static.py:235-304) against outputs of the reference class itself (tests/golden/ref_static.npz,
+    made by tools/make_golden_static.py): contexts grow from the zero row to 40 frames."""
+    from vap_realtime_b200.vap_static import VAPRealTimeStatic
+
+    fx = np.load(os.path.join(GOLDEN, "ref_vap_ctx2500.npz"))
+    ref = np.load(os.path.join(GOLDEN, "ref_static.npz"))
+    a32 = fx["audio"].astype(np.float32) / 32768.0
+    m = VAPRealTimeStatic(built_asset("vap_jp_20hz_2500msec.vapw"), None, torch.device("cuda", 0), 20, 5.0)
+    e1c = torch.zeros(1, 1, 256)
+    e2c = torch.zeros(1, 1, 256)
+    worst_p, worst_e = 0.0, 0.0
+    for n in range(ref["p_now"].shape[0]):
+        x = a32[:, 800 * n: 800 * n + 1120]
+        p_now, p_fut, v1, v2, e1, e2 = m.forward(torch.from_numpy(x[0].copy()).view(1, 1, -1), torch.from_numpy(x[1].copy()).view(1, 1, -1), e1c, e2c)
+        assert p_now.shape == (1, 2) and p_fut.shape == (1, 2) and v1.shape == (1, 1) and e1.shape == (1, 1, 256)
+        got = np.concatenate([p_now.numpy()[0], p_fut.numpy()[0], v1.numpy()[0], v2.numpy()[0]])
+        want = np.concatenate([ref["p_now"][n], ref["p_future"][n], ref["vad"][n]])
+        worst_p = max(worst_p, float(np.abs(got - want).max()))
+        worst_e = max(worst_e, float(np.abs(np.stack([e1.numpy()[0, 0], e2.numpy()[0, 0]]) - ref["e"][n]).max()))
+        e1c = torch.cat([e1c, e1], dim=1)[:, -99:]          # the caller owns the contexts (vap_static.py:239-245)
+        e2c = torch.cat([e2c, e2], dim=1)[:, -99:]
+    print(f"stateless forward vs reference VAPRealTimeStatic: p/vad {worst_p:.2e}, embeddings {worst_e:.2e}")
+    assert worst_p < 1e-4
+    assert worst_e < 3e-4
