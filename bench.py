@@ -5,10 +5,15 @@
     python bench.py --impl reference --gpus N ...            # the CPU path (oracle port) on host cores
 
 A "step" = one process_vap pass over one batch of B streams per GPU
-(reference rvap/vap_main/vap_main.py:249-335).  Workload at N=1: BASELINE.json
-configs[1] (batch=64 concurrent stereo streams, 20 Hz / 2.5 s context, 1xB200).
-For N>1 every rank runs its own B streams (streams are independent: stream s
-lives on one GPU for its lifetime), results are gathered on rank 0 with NCCL.
+(reference rvap/vap_main/vap_main.py:249-335).  Workload: --config selects a
+BASELINE.json configuration (default 2 = configs[1], batch=64 concurrent stereo
+streams, 20 Hz / 2.5 s context, 1xB200; 3 = 128 streams per GPU (1024 over 8);
+4 = batch 256 at 5.0 s context; 5 = vap_bc head, 64 streams per GPU at 5.0 s).
+For N>1 the streams are partitioned over the ranks (stream s lives on one GPU for
+its lifetime) and rank 0 is the ingest rank, as north_star words it: every step
+the input windows [N*B, 2, 1120] are scattered from rank 0 and the [N*B, 6]
+results gathered back over NCCL, double-buffered on a side stream so that both
+exchanges overlap the neighbouring steps (vap_realtime_b200/dist.py).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
 """
@@ -55,6 +60,19 @@ def stream_kernel_gflop_per_frame(T: int) -> float:
     return 2.0 * macs / 1e9
 
 
+# --config: BASELINE.json configs[1..4] (configs[0] is the reference's own single-pair CPU case: tests/, not a bench line)
+CONFIGS = {
+    2: {"batch_per_gpu": 64, "ctx_frames": 50, "head": "vap",
+        "label": "BASELINE configs[1]: batch=64 concurrent stereo streams, 20 Hz / 2.5 s context, 1xB200"},
+    3: {"batch_per_gpu": 128, "ctx_frames": 50, "head": "vap",
+        "label": "BASELINE configs[2]: batch=1024 streams, 20 Hz / 2.5 s context, sharded across 8xB200 = 128 streams per GPU"},
+    4: {"batch_per_gpu": 256, "ctx_frames": 100, "head": "vap",
+        "label": "BASELINE configs[3]: batch=256 streams, 20 Hz / 5.0 s context (jp_20hz_2500msec weights, T=100), 1xB200"},
+    5: {"batch_per_gpu": 64, "ctx_frames": 100, "head": "bc",
+        "label": "BASELINE configs[4]: vap_bc backchannel head (erica_20hz_5000msec, T=100), batch=512 over 8xB200 = 64 streams per GPU"},
+}
+
+
 def load_weights(head: str):
     """Real checkpoint when the built assets travelled with the repo, else random-init
     weights of the same architecture (the arithmetic per step is identical)."""
@@ -68,10 +86,11 @@ def load_weights(head: str):
 
 def make_audio(n_streams: int, n_chunks: int, first_stream: int = 0) -> np.ndarray:
     """[n_chunks, n_streams, 2, 1120] synthetic 16 kHz stereo (seed 1234+s, 0.05*randn clamped)."""
-    from oracle.vap_oracle import synthetic_audio   # input generator only (not the arithmetic under test)
+    import torch
     out = np.empty((n_chunks, n_streams, 2, 1120), dtype=np.float32)
     for s in range(n_streams):
-        a = synthetic_audio(first_stream + s, n_chunks, FRAME_HZ)
+        g = torch.Generator().manual_seed(1234 + first_stream + s)
+        a = (torch.randn(2, 800 * n_chunks + 320, generator=g) * 0.05).clamp_(-1, 1).numpy()
         for n in range(n_chunks):
             out[n, s] = a[:, 800 * n: 800 * n + 1120]
     return out
@@ -166,22 +185,25 @@ def run_reference(args):
     if rank != 0:
         return 0
     import torch
-    B, T = args.batch_per_gpu * 1, args.ctx_frames       # same per-step workload as our arm at N=1
+    Bg, T = args.batch_per_gpu * args.gpus, args.ctx_frames       # the same GLOBAL stream count per step as our arm
+    B = Bg
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     cores = torch.get_num_threads()
-    # bounded sample: if K full-batch steps would not finish within ~2 minutes, each step times 16 of the B streams
-    _, probe = cpu_step_rate(B, T, args.head, 1, 1)
-    if probe[0] * (args.steps + args.warmup) > 120.0:
-        B = min(B, 16)
+    # bounded sample: while K steps of the sample would not finish within ~2 minutes, the sample is halved (the
+    # oracle port's frames/s is flat in B above ~16 streams, so the sample rate stands for the full batch)
+    _, probe = cpu_step_rate(min(B, 64), T, args.head, 1, 1)
+    per_stream = probe[0] / min(B, 64)
+    while B > 16 and per_stream * B * (args.steps + args.warmup) > 120.0:
+        B //= 2
     fps, times = cpu_step_rate(B, T, args.head, args.steps, max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steady-state steps of B={B} streams (T={T}), oracle port of process_vap batched "
-                                   f"over the streams, torch CPU {torch.__version__}, {cores} intra-op threads"},
+                         "sample": f"{args.steps} steady-state steps of B={B} of the {Bg} global streams (T={T}), oracle port of process_vap "
+                                   f"batched over the streams, torch CPU {torch.__version__}, {cores} intra-op threads"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count()},
     }
@@ -191,11 +213,15 @@ def run_reference(args):
 
 def workload_config(args, n_gpus):
     return {
-        "workload": f"batch={args.batch_per_gpu} concurrent stereo streams per GPU, 20 Hz / {args.ctx_frames / FRAME_HZ:.1f} s context "
-                    f"(BASELINE configs[1] at N=1)",
+        "workload": f"{args.label}; run here as batch={args.batch_per_gpu} concurrent stereo streams per GPU x {n_gpus} GPU(s), "
+                    f"20 Hz / {args.ctx_frames / FRAME_HZ:.1f} s context, head {args.head}",
+        "baseline_config": args.config,
         "streams_per_gpu": args.batch_per_gpu, "global_streams": args.batch_per_gpu * n_gpus, "ctx_frames": args.ctx_frames,
-        "frame_hz": FRAME_HZ, "head": args.head, "sharding": f"streams partitioned over {n_gpus} GPU(s), no data-path collective; "
-                                                             "NCCL gather of [B,6] results to rank 0",
+        "frame_hz": FRAME_HZ, "head": args.head,
+        "sharding": ("one GPU, no collective" if n_gpus == 1 else
+                     f"streams partitioned over {n_gpus} GPUs (stream affinity, no collective inside the step); rank 0 ingests: NCCL scatter of the "
+                     f"[{args.batch_per_gpu * n_gpus},2,1120] windows and NCCL all-gather of the [B,6] results every step, double-buffered on a "
+                     "side stream (overlapping the neighbouring steps)"),
         "l2": "flushed between timed steps (256 MiB memset outside the per-step events)",
     }
 
@@ -229,80 +255,135 @@ def run_ours(args):
 
     n_chunks = T + W + K + 2
     pool = min(n_chunks, 16)                                  # distinct input chunks cycled through
-    audio_h = torch.from_numpy(make_audio(B, pool, first_stream=rank * B)).pin_memory()      # [pool, B, 2, 1120]
-    audio_d = audio_h.to(dev)
-    out_d = torch.empty((B, 6), device=dev)
-    gathered = torch.empty((world * B, 6), device=dev) if world > 1 else None
+    Bg = world * B                                            # global streams; rank 0 is the ingest rank for N > 1
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    main = torch.cuda.current_stream(dev)
+    step_i = 0
+    if world == 1:
+        audio_h = torch.from_numpy(make_audio(B, pool)).pin_memory()                  # [pool, B, 2, 1120]
+        audio_d = audio_h.to(dev)
+        out_d = torch.empty((B, 6), device=dev)
 
-    def gather():
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out_d)
+        def one_step():
+            nonlocal step_i
+            eng.step(audio_d[step_i % pool], out=out_d)
+            step_i += 1
+
+        drain = lambda: None
+    else:
+        from vap_realtime_b200.dist import ShardedVap
+        sv = ShardedVap(None, Bg, 1120, dev)
+        pipe = sv.pipeline(lambda a, o: eng.step(a, out=o))
+        audio_h = torch.from_numpy(make_audio(Bg, pool)).pin_memory() if rank == 0 else None      # [pool, N*B, 2, 1120]
+        audio_d = audio_h.to(dev) if rank == 0 else None
+        audio_local_d = torch.from_numpy(make_audio(B, pool, first_stream=rank * B)).to(dev)      # prefill only (no exchange)
+        out_d = torch.empty((B, 6), device=dev)
+
+        def one_step(host=False):
+            nonlocal step_i
+            src = (audio_h if host else audio_d)
+            k = pipe.push(src[step_i % pool] if rank == 0 else None)
+            step_i += 1
+            return k
+
+        drain = pipe.drain
 
     # window full (steady state) + warm-up; graph capture happens on the first call per input buffer
-    step_i = 0
-    for _ in range(T):
-        eng.step(audio_d[step_i % pool], out=out_d)
-        step_i += 1
-    for _ in range(max(W, 3)):
-        eng.step(audio_d[step_i % pool], out=out_d)
-        gather()
-        step_i += 1
+    for i in range(T):
+        if world == 1:
+            one_step()
+        else:
+            eng.step(audio_local_d[i % pool], out=out_d)
+    for _ in range(max(W, 3) + 2):
+        one_step()
+    drain()
     torch.cuda.synchronize()
     launches_per_step = eng.last_launch_count
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
 
-    # ---- device-resident timing: per-step events, L2 flushed between steps
+    # ---- device-resident timing: per-step events on the launching stream, L2 flushed between steps.  For N > 1 the
+    # events bracket "wait for this step's scattered windows + step"; scatter n+1 / gather n-1 run on the side stream
+    # meanwhile, and the drain of the last gather is added once at the end.
     sampler = ClockSampler(local)
     sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev_tail = torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.zero_()
         ev[i][0].record()
-        eng.step(audio_d[step_i % pool], out=out_d)
-        gather()
+        one_step()
         ev[i][1].record()
-        step_i += 1
+    drain()
+    ev_tail.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = float(step_ms.sum())
+    tail_ms = ev[K - 1][1].elapsed_time(ev_tail) if world > 1 else 0.0
+    total_ms = float(step_ms.sum()) + tail_ms
 
     # ---- back-to-back (no flush) for reference
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        eng.step(audio_d[step_i % pool], out=out_d)
-        gather()
-        step_i += 1
+        one_step()
+    drain()
     e1.record()
     torch.cuda.synchronize()
     b2b_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + step + D2H every step
-    out_h = torch.empty((B, 6), dtype=torch.float32).pin_memory()
-    for i in range(3):
-        eng.step_host(audio_h[step_i % pool], out=out_h)
-        step_i += 1
-    torch.cuda.synchronize()
-    if world > 1:
+    # ---- end to end with HOST buffers (pinned), host<->device copies inside the timed region, every step:
+    #   N = 1: vapb_step_host (H2D of [B,2,1120], step, D2H of [B,6], synchronous)
+    #   N > 1: ShardedPipeline.push(pinned host windows of all N*B streams on rank 0) -> H2D, scatter, step, gather;
+    #          rank 0 copies the gathered [N*B,6] of the previous step to pinned host memory and waits for it
+    if world == 1:
+        out_h = torch.empty((B, 6), dtype=torch.float32).pin_memory()
+        for i in range(3):
+            eng.step_host(audio_h[step_i % pool], out=out_h)
+            step_i += 1
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            eng.step_host(audio_h[step_i % pool], out=out_h)
+            step_i += 1
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_api = "vapb_step_host via VapEngine.step_host (pinned host buffers, synchronous)"
+        h2d, d2h = B * 2 * 1120 * 4, B * 6 * 4
+    else:
+        out_h = torch.empty((Bg, 6), dtype=torch.float32).pin_memory()
+
+        def e2e_loop(n):
+            for i in range(n):
+                k = one_step(host=True)
+                if k >= 1 and rank == 0:
+                    out_h.copy_(pipe.results(k - 1), non_blocking=True)
+                    torch.cuda.current_stream(dev).synchronize()
+            k_last = pipe.n - 1
+            res = pipe.results(k_last)
+            if rank == 0:
+                out_h.copy_(res, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_loop(3)
         dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        eng.step_host(audio_h[step_i % pool], out=out_h)
-        step_i += 1
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        e2e_loop(K)
+        dist.barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_api = ("dist.ShardedPipeline.push on rank 0 with pinned host windows of all N*B streams: H2D, NCCL scatter, vapb_step on every "
+                   "rank, NCCL all-gather, D2H of the [N*B,6] results on rank 0 (double-buffered, one step of latency)")
+        h2d, d2h = Bg * 2 * 1120 * 4, Bg * 6 * 4
+    audio_d = audio_d if world == 1 else audio_local_d
 
     # ---- per-kernel-class breakdown (one eager step with events behind every launch)
     prof = eng.profile_step(audio_d[step_i % pool], out=out_d)
@@ -357,8 +438,7 @@ def run_ours(args):
             "realtime_streams": value / FRAME_HZ,
             "back_to_back_ms_per_step": b2b_ms / K,
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
-            "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 2 * 1120 * 4, "d2h_bytes_per_step": B * 6 * 4,
-                    "api": "vapb_step_host via VapEngine.step_host (pinned host buffers, synchronous)"},
+            "e2e": {"value": frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,

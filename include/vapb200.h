@@ -9,8 +9,14 @@
  * and, in functional form, tools/vap_static.py:235-304.  Each entry point below
  * names the reference code it replaces.  All functions return 0 on success and
  * a negative VAPB_E* code on failure (never throw); vapb_last_error() gives
- * the text.  A handle is NOT thread-safe; use one handle per CUDA device and
- * call it from one thread at a time.
+ * the text.
+ *
+ * Threading contract: a handle is NOT thread-safe; call it from one thread at
+ * a time.  Different handles (same or different devices) may be driven from
+ * different threads concurrently: the library keeps no process-global mutable
+ * state (per-call launch flags are thread-local).  vapb_reset_streams,
+ * vapb_export_state and vapb_import_state synchronise the whole device before
+ * they return, so a following vapb_step may use any CUDA stream.
  *
  * Signatures carry plain pointers and sizes only (no torch / C++ types).
  */
@@ -83,6 +89,9 @@ VAPB_API int vapb_reset_streams(vapb_handle h, const int* stream_ids, int n);
  *                  VAPB_HEAD_BC : p_bc_react, p_bc_emo, 0, 0, 0, 0 (vap_bc_main.py:276-284)
  *   cuda_stream: cudaStream_t the work is enqueued on (asynchronous; the
  *                caller synchronises).  May be NULL (legacy default stream).
+ * The step replays one CUDA graph per batch size B (captured on first use, LRU over 96 sizes); `audio` and
+ * `out` are read through a small device record refreshed by the same host->device copy that carries the
+ * stream ids, so callers may pass different buffers on every call at no cost.
  */
 VAPB_API int vapb_step(vapb_handle h, const float* audio, const int* stream_ids, int B, float* out,
               void* cuda_stream);

@@ -33,7 +33,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_streams, n_steps, q):
+def _worker(rank, world, port, n_streams, n_steps, q, pipelined=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -50,6 +50,20 @@ def _worker(rank, world, port, n_streams, n_steps, q):
     sv = ShardedVap(lambda a: oracle.step(a, st), n_streams, 1120, torch.device("cpu"))
     audio = np.stack([synthetic_audio(s, n_steps) for s in range(n_streams)])
     outs = []
+    if pipelined:
+        # double-buffered root-ingest loop (ShardedPipeline): push n, read the results of push n - 1
+        def step_into(a, o):
+            o.copy_(oracle.step(a, st))
+        pipe = sv.pipeline(step_into)
+        for n in range(n_steps):
+            chunk = torch.from_numpy(np.ascontiguousarray(audio[:, :, 800 * n: 800 * n + 1120]))
+            k = pipe.push(chunk if rank == 0 else None)
+            if k >= 1:
+                outs.append(pipe.results(k - 1).clone())
+        outs.append(pipe.results(n_steps - 1).clone())
+        with pytest.raises(ValueError):
+            pipe.results(0)
+        n_steps = 0
     for n in range(n_steps):
         chunk = torch.from_numpy(np.ascontiguousarray(audio[:, :, 800 * n: 800 * n + 1120]))
         if n % 2 == 0:       # root-ingest mode: only rank 0 sees the windows
@@ -63,8 +77,8 @@ def _worker(rank, world, port, n_streams, n_steps, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_streams", [4, 5])
-def test_world2_scatter_step_gather(n_streams):
+@pytest.mark.parametrize("n_streams,pipelined", [(4, False), (5, False), (4, True), (5, True)])
+def test_world2_scatter_step_gather(n_streams, pipelined):
     from oracle.vap_oracle import OracleState, VapOracle, synthetic_audio
     from vap_realtime_b200 import weights
 
@@ -72,7 +86,7 @@ def test_world2_scatter_step_gather(n_streams):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_streams, n_steps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_streams, n_steps, q, pipelined)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=240)

@@ -41,6 +41,14 @@ inline RowMap plain_map(long long ld, long long offset = 0) {
     return m;
 }
 
+// Caller-owned buffers of one step, read by the kernels THROUGH device memory when the step runs as a CUDA graph:
+// the graph is captured once per batch size and vapb_step only rewrites these two pointers (same small H2D copy
+// that carries the stream ids), so callers may pass any audio / out buffer without a re-capture.
+struct IoPtrs {
+    const float* audio;   // [B][2][S]
+    float* out;           // [B][6]
+};
+
 struct GemmArgs {
     const float* A;
     RowMap amap;          // row m of A (K contiguous floats)
@@ -97,8 +105,8 @@ struct OncePerDevice {
     }
 };
 
-extern bool g_use_pdl;      // set by the step driver before it enqueues kernels
-extern bool g_attn_rk;
+extern thread_local bool g_use_pdl;      // set by the step driver before it enqueues kernels
+extern thread_local bool g_attn_rk;
 
 // (A uniform max-shared-memory carve-out hint for every kernel was tried and measured ~5 % slower:
 //  the row-wise kernels lose their L1.  profiles/r01_j_option_ablation.log)
@@ -141,8 +149,8 @@ inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 #endif
 
 // ---- launchers implemented in kernels_simt.cu -------------------------------------------
-void launch_conv0(const float* audio, int n_chunks, int S, int L0, const float* w, const float* b,
-                  const float* cnw, const float* cnb, float* out, RowMap omap, cudaStream_t st);
+void launch_conv0(const float* audio, const IoPtrs* io, int n_chunks, int S, int L0, const float* w, const float* b,
+                  const float* cnw, const float* cnb, float* out, RowMap omap, cudaStream_t st);      // io != null: audio = io->audio
 void launch_sgemm(const GemmArgs& g, cudaStream_t st);
 void launch_cn_relu(float* X, RowMap map, int M, const float* w, const float* b, cudaStream_t st,
                     const float* partials = nullptr, int nsplit = 0, long long split_stride = 0);
@@ -176,7 +184,7 @@ void launch_attention(const AttnArgs& a, cudaStream_t st);
 // last-row-only variants used when the final cross layer is pruned to the newest frame
 void launch_gather_last(const float* X, const int* tvalid, float* Xl, int n_seq, int T, cudaStream_t st);
 void launch_attention_last(const AttnArgs& a, cudaStream_t st);   // Q, O: [n_seq][256] compact; K, V: full rows
-void launch_vad(const float* X, const int* tvalid, const float* w, const float* b, float* out, int B, int T,
+void launch_vad(const float* X, const int* tvalid, const float* w, const float* b, float* out, const IoPtrs* io, int B, int T,
                 cudaStream_t st);
 struct HeadArgs {
     const float* X;            // [2B*T][256] final cross-layer output
@@ -184,6 +192,7 @@ struct HeadArgs {
     const float* Wa; const float* Wb; const float* lnw; const float* lnb;
     const float* Wh; const float* bh; int n_out;   // 256 (vap) or 3 (bc)
     float* out;                // [B][6]
+    const IoPtrs* io;          // != null: out = io->out
     float* comb_tap;           // [B][256] or nullptr
     float* logits_tap;         // [B][256] or nullptr
     int* count; const int* ids;

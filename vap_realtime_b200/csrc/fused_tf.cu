@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
                     s = fmaf(x0.x, w0.x, s); s = fmaf(x0.y, w0.y, s); s = fmaf(x0.z, w0.z, s); s = fmaf(x0.w, w0.w, s);
                     s = fmaf(x1.x, w1.x, s); s = fmaf(x1.y, w1.y, s); s = fmaf(x1.z, w1.z, s); s = fmaf(x1.w, w1.w, s);
                     s = warp_sum_f(s) + __ldg(p.va_b);
-                    if (c.lane == 0) p.out[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
+                    if (c.lane == 0) (p.io ? p.io->out : p.out)[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
                 } else if (side == FSIDE_GATHER_LAST) {
                     // newest frame of channel r -> one row per sequence for the pruned layer's tail
                     const int n = 2 * c.b + c.r;

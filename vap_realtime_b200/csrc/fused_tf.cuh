@@ -66,6 +66,7 @@ struct FusedParams {
     const float* va_w;
     const float* va_b;
     float* out;              // [B][6]
+    const IoPtrs* io;        // != null: out = io->out (graph launches)
     long long* dbg;          // optional clock64 stamps: [n_ops + 1] of cluster 0 / CTA 0, fine stamps of op dbg_op at [40..52)
     int dbg_op;
 };

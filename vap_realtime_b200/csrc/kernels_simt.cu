@@ -14,8 +14,8 @@
 
 namespace vapb {
 
-bool g_use_pdl = false;
-bool g_attn_rk = true;      // register-resident-K attention for T <= 64 (option "attn_rk")
+thread_local bool g_use_pdl = false;      // per thread: two handles may be driven from two threads
+thread_local bool g_attn_rk = true;      // register-resident-K attention for T <= 64 (option "attn_rk")
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -50,7 +50,7 @@ __device__ __forceinline__ void store_row8(float* p, int lane, const float v[8])
 // -----------------------------------------------------------------------------------------
 constexpr int kC0PosPerBlock = 56;
 
-__global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__ audio, int S, int L0,
+__global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__ audio, const IoPtrs* __restrict__ io, int S, int L0,
                                                        const float* __restrict__ w,    // [10][256] tap-major
                                                        const float* __restrict__ b,
                                                        const float* __restrict__ cnw,
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__
     const int npos = min(kC0PosPerBlock, L0 - p0);
     const int first = 5 * p0 - 3;
     const int need = 5 * (npos - 1) + 10;
-    const float* a = audio + (size_t)chunk * S;
+    const float* a = (io ? io->audio : audio) + (size_t)chunk * S;
     for (int i = threadIdx.x; i < need; i += blockDim.x) {
         int s = first + i;
         s_in[i] = (s >= 0 && s < S) ? a[s] : 0.0f;
@@ -114,10 +114,10 @@ __global__ void __launch_bounds__(256) k_conv0_cn_relu(const float* __restrict__
     }
 }
 
-void launch_conv0(const float* audio, int n_chunks, int S, int L0, const float* w, const float* b,
+void launch_conv0(const float* audio, const IoPtrs* io, int n_chunks, int S, int L0, const float* w, const float* b,
                   const float* cnw, const float* cnb, float* out, RowMap omap, cudaStream_t st) {
     dim3 grid((L0 + kC0PosPerBlock - 1) / kC0PosPerBlock, n_chunks);
-    launch_k(k_conv0_cn_relu, grid, dim3(256), 0, st, audio, S, L0, w, b, cnw, cnb, out, omap);
+    launch_k(k_conv0_cn_relu, grid, dim3(256), 0, st, audio, io, S, L0, w, b, cnw, cnb, out, omap);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -1073,9 +1073,10 @@ void launch_attention_last(const AttnArgs& a, cudaStream_t st) {
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vad(const float* __restrict__ X, const int* __restrict__ tvalid,
                                              const float* __restrict__ w, const float* __restrict__ b,
-                                             float* __restrict__ out, int B, int T) {
+                                             float* __restrict__ out_direct, const IoPtrs* __restrict__ io, int B, int T) {
     pdl_trigger();
     pdl_wait();
+    float* out = io ? io->out : out_direct;
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (n >= 2 * B) return;
     const int lane = threadIdx.x & 31;
@@ -1089,9 +1090,9 @@ __global__ void __launch_bounds__(256) k_vad(const float* __restrict__ X, const 
     s = warp_sum(s) + b[0];
     if (lane == 0) out[(n >> 1) * 6 + 4 + (n & 1)] = sigmoidf_(s);
 }
-void launch_vad(const float* X, const int* tvalid, const float* w, const float* b, float* out, int B, int T,
+void launch_vad(const float* X, const int* tvalid, const float* w, const float* b, float* out, const IoPtrs* io, int B, int T,
                 cudaStream_t st) {
-    launch_k(k_vad, dim3((2 * B + 7) / 8), dim3(256), 0, st, X, tvalid, w, b, out, B, T);
+    launch_k(k_vad, dim3((2 * B + 7) / 8), dim3(256), 0, st, X, tvalid, w, b, out, io, B, T);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -1195,7 +1196,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_head(HeadArgs a) {
     }
     __syncthreads();
     if (a.logits_tap && tid < a.n_out) a.logits_tap[(size_t)b * kD + tid] = sl[tid];
-    float* out = a.out + (size_t)b * 6;
+    float* out = (a.io ? a.io->out : a.out) + (size_t)b * 6;
     if (a.head_kind == 0) {
         // softmax over 256 classes, then p[s] = sum_c pi_c * (#active bins of speaker s in the range)
         if (warp < 8) {

@@ -61,13 +61,13 @@ struct LayerWeights {
     TcWeight tc_q_c, tc_kv_c, tc_proj_c;
 };
 
-struct GraphEntry {
+struct GraphEntry {          // one captured step per batch size (audio / out are read through IoPtrs in device memory)
     int B;
-    const float* audio;
-    float* out;
     cudaGraphExec_t exec;
     int launches;
+    unsigned long long last_used;
 };
+constexpr size_t kMaxGraphs = 96;      // LRU beyond that (a server's batch size wanders between 1 and max_batch)
 
 }  // namespace
 
@@ -98,8 +98,12 @@ struct vapb_ctx {
     int* count = nullptr;
 
     // per-step workspaces (sized for max_batch)
+    uint8_t* iobuf_dev = nullptr;    // [IoPtrs (16 B)][ids: max_batch x int32], refreshed by ONE H2D copy per step
+    uint8_t* iobuf_pinned = nullptr;
+    IoPtrs* io_dev = nullptr;
     int* ids_dev = nullptr;
-    int* ids_pinned = nullptr;
+    int sm_count = 148;
+    unsigned long long tick = 0;
     int* tvalid = nullptr;
     float* act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // channels-last, with halo rows
     int halo[5] = {0, 0, 0, 0, 0};
@@ -172,7 +176,7 @@ bool parse_blob(const void* blob, size_t nbytes, std::map<std::string, HostTenso
     uint32_t n, tb;
     memcpy(&n, p + 8, 4);
     memcpy(&tb, p + 12, 4);
-    if (tb != n * 96u || 16 + (size_t)tb > nbytes) {
+    if ((uint64_t)n * 96u != (uint64_t)tb || 16 + (uint64_t)tb > (uint64_t)nbytes) {
         err = "weight blob: corrupt table";
         return false;
     }
@@ -189,7 +193,9 @@ bool parse_blob(const void* blob, size_t nbytes, std::map<std::string, HostTenso
         uint32_t nb;
         memcpy(&off, e + 84, 8);
         memcpy(&nb, e + 92, 4);
-        if (ndim > 4 || off + nb > nbytes || (off & 3)) {
+        uint64_t prod = 1;
+        for (uint32_t d = 0; d < ndim && d < 4; ++d) prod *= t.dims[d];
+        if (ndim > 4 || off > (uint64_t)nbytes || (uint64_t)nb > (uint64_t)nbytes - off || (off & 3) || prod * 4 != (uint64_t)nb) {
             err = std::string("weight blob: bad entry ") + name;
             return false;
         }
@@ -318,6 +324,7 @@ struct Step {
     int B;
     const float* audio;
     float* out;
+    const IoPtrs* io = nullptr;     // graph capture: kernels read audio / out through this device record instead
     int n = 0;      // launches
     std::vector<std::pair<const char*, cudaEvent_t>>* prof = nullptr;   // per-launch events (vapb_profile_step)
 };
@@ -531,7 +538,7 @@ void fused_transformer(Step& s) {
     FusedParams p;
     p.ops = c->fops; p.n_ops = c->n_fops; p.T = c->T; p.mode = (2 * c->T <= 128) ? 0 : 1;
     p.ring = c->ring; p.count = c->count; p.ids = c->ids_dev; p.tvalid = c->tvalid; p.X = c->X; p.Xl = c->Xl;
-    p.va_w = c->va_w; p.va_b = c->va_b; p.out = s.out;
+    p.va_w = c->va_w; p.va_b = c->va_b; p.out = s.out; p.io = s.io;
     p.ds_part = c->fused_ds_part; p.ds_stride = c->fused_ds_stride; p.ds_nsplit = c->fused_ds_nsplit;
     p.ds_lnw = c->ds_lnw; p.ds_lnb = c->ds_lnb; p.e_out = c->ebuf;
     p.dbg = c->opt_fused_dbg ? c->fused_clk : nullptr;
@@ -548,7 +555,7 @@ void enqueue_step(Step& s) {
     cudaStream_t st = s.st;
 
     // ---- CPC encoder on the newest chunk (encoder.py:58-80)
-    launch_conv0(s.audio, NC, c->S, c->L[0], c->w0, c->b0, c->cn0w, c->cn0b, c->act[0], act_map(c, 0), st); mark(s, "conv0_cn_relu");
+    launch_conv0(s.audio, s.io, NC, c->S, c->L[0], c->w0, c->b0, c->cn0w, c->cn0b, c->act[0], act_map(c, 0), st); mark(s, "conv0_cn_relu");
     for (int i = 0; i < 4; ++i) {
         const ConvLayer& cv = c->conv[i];
         // im2col-free: output row p of a chunk reads k*256 contiguous floats starting at input
@@ -604,7 +611,7 @@ void enqueue_step(Step& s) {
     // one cluster per stream: a win while all clusters are co-resident (2B <= SM count); bigger batches are served
     // better by the batched per-op kernels, whose GEMM tiles are full (measured B = 128 / 256: r01_n_experiments.md)
     const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
-    const bool use_stream = c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (2 * B <= 148 || c->opt_fused == 2);
+    const bool use_stream = c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (2 * B <= c->sm_count || c->opt_fused == 2);
     // ---- downsample conv over exactly n_lstm frames + LayerNorm + GELU -> ring
     {
         const int Kd = c->n_lstm * kD;
@@ -636,7 +643,7 @@ void enqueue_step(Step& s) {
     transformer_layer(s, c->layers[0]);
     tap_copy(s, c->tap_chan, c->X, RX);
     if (c->head_kind == VAPB_HEAD_VAP) {
-        launch_vad(c->X, c->tvalid, c->va_w, c->va_b, s.out, B, T, st); mark(s, "vad");
+        launch_vad(c->X, c->tvalid, c->va_w, c->va_b, s.out, s.io, B, T, st); mark(s, "vad");
     }
     // ---- ar: three TransformerStereoLayers (modules.py:289-300, 395-423)
     for (int li = 0; li < 3; ++li) {
@@ -648,7 +655,7 @@ void enqueue_step(Step& s) {
     // ---- combinator + projection head + aggregation; advances the frame counters
     HeadArgs h;
     h.X = prune ? c->Xl : c->X; h.compact = prune ? 1 : 0; h.tvalid = c->tvalid; h.Wa = c->Wa; h.Wb = c->Wb; h.lnw = c->comb_lnw; h.lnb = c->comb_lnb;
-    h.Wh = c->Wh; h.bh = c->bh; h.n_out = c->n_out; h.out = s.out;
+    h.Wh = c->Wh; h.bh = c->bh; h.n_out = c->n_out; h.out = s.out; h.io = s.io;
     h.comb_tap = c->opt_keep_taps ? c->tap_comb : nullptr;
     h.logits_tap = c->opt_keep_taps ? c->tap_logits : nullptr;
     h.count = c->count; h.ids = c->ids_dev; h.B = B; h.T = T; h.head_kind = c->head_kind;
@@ -698,10 +705,11 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         return fail(nullptr, VAPB_EUNSUPPORTED, "device %d is sm_%d%d; libvapb200 is built for sm_100a only", device,
                     prop.major, prop.minor);
     if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, VAPB_ECUDA, "cudaSetDevice failed");
+    const int sm_count = prop.multiProcessorCount;
 
     vapb_ctx* c = new vapb_ctx();
     c->device = device; c->frame_hz = frame_hz; c->T = ctx_frames; c->max_streams = max_streams;
-    c->max_batch = max_batch; c->head_kind = head_kind;
+    c->max_batch = max_batch; c->head_kind = head_kind; c->sm_count = sm_count;
     c->S = 16000 / frame_hz + kPadSamples;
     const int ck[5] = {10, 8, 4, 4, 4}, cs[5] = {5, 4, 2, 2, 2}, cp[5] = {3, 2, 1, 1, 1};
     int len = c->S;
@@ -788,7 +796,7 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     DA(c->cS, MS * 2 * kD);
     DA(c->ring, MS * 2 * c->T * kD);
     DA(c->count, MS);
-    DA(c->ids_dev, MB);
+    DA(c->iobuf_dev, sizeof(IoPtrs) + MB * sizeof(int));
     DA(c->tvalid, MB);
     for (int i = 0; i < 5; ++i) DA(c->act[i], NC * (size_t)(c->L[i] + 2 * c->halo[i]) * kD);
     DA(c->hW, NC * kD);
@@ -820,7 +828,10 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         vapb_destroy(c);
         return rc;
     }
-    if (cudaMallocHost(reinterpret_cast<void**>(&c->ids_pinned), MB * sizeof(int)) != cudaSuccess)
+    static_assert(sizeof(IoPtrs) == 16, "IoPtrs layout");
+    c->io_dev = reinterpret_cast<IoPtrs*>(c->iobuf_dev);
+    c->ids_dev = reinterpret_cast<int*>(c->iobuf_dev + sizeof(IoPtrs));
+    if (cudaMallocHost(reinterpret_cast<void**>(&c->iobuf_pinned), sizeof(IoPtrs) + MB * sizeof(int)) != cudaSuccess)
         FAIL_CREATE(VAPB_ENOMEM, "cudaMallocHost failed");
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
@@ -872,7 +883,7 @@ int vapb_destroy(vapb_handle h) {
     cudaDeviceSynchronize();
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->ids_pinned) cudaFreeHost(h->ids_pinned);
+    if (h->iobuf_pinned) cudaFreeHost(h->iobuf_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
@@ -897,6 +908,7 @@ int vapb_reset_streams(vapb_handle h, const int* ids, int n) {
         CK(h, cudaMemset(h->cS, 0, st * h->max_streams));
         CK(h, cudaMemset(h->ring, 0, rg * h->max_streams));
         CK(h, cudaMemset(h->count, 0, sizeof(int) * h->max_streams));
+        CK(h, cudaDeviceSynchronize());      // the memsets ran on the legacy stream: later steps may use any stream
         return VAPB_OK;
     }
     for (int i = 0; i < n; ++i) {
@@ -907,6 +919,7 @@ int vapb_reset_streams(vapb_handle h, const int* ids, int n) {
         CK(h, cudaMemset(h->ring + (size_t)id * 2 * h->T * kD, 0, rg));
         CK(h, cudaMemset(h->count + id, 0, sizeof(int)));
     }
+    CK(h, cudaDeviceSynchronize());
     return VAPB_OK;
 }
 
@@ -925,19 +938,24 @@ int vapb_step(vapb_handle h, const float* audio, const int* ids, int B, float* o
         CK(h, cudaEventRecord(h->ev_in, caller));
         CK(h, cudaStreamWaitEvent(st, h->ev_in, 0));
     }
-    // ids -> device.  The pinned staging buffer is reused, so wait for the previous copy first.
+    // {audio, out} + ids -> device in ONE copy.  The pinned staging buffer is reused, so wait for the previous copy first.
     if (h->last_B != 0) CK(h, cudaEventSynchronize(h->ev0));
-    memcpy(h->ids_pinned, ids, sizeof(int) * B);
-    CK(h, cudaMemcpyAsync(h->ids_dev, h->ids_pinned, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    {
+        IoPtrs io{audio, out};
+        memcpy(h->iobuf_pinned, &io, sizeof io);
+        memcpy(h->iobuf_pinned + sizeof io, ids, sizeof(int) * B);
+        CK(h, cudaMemcpyAsync(h->iobuf_dev, h->iobuf_pinned, sizeof io + sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    }
     CK(h, cudaEventRecord(h->ev0, st));
     h->last_B = B;
 
     if (use_graph) {
         GraphEntry* ge = nullptr;
         for (auto& g : h->graphs)
-            if (g.B == B && g.audio == audio && g.out == out) ge = &g;
+            if (g.B == B) ge = &g;
         if (!ge) {
-            Step s{h, st, B, audio, out};
+            Step s{h, st, B, nullptr, nullptr};
+            s.io = h->io_dev;
             cudaGraph_t graph = nullptr;
             CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             enqueue_step(s);
@@ -947,13 +965,17 @@ int vapb_step(vapb_handle h, const float* audio, const int* ids, int B, float* o
             e = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return fail(h, VAPB_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-            if (h->graphs.size() >= 16) {
-                cudaGraphExecDestroy(h->graphs.front().exec);
-                h->graphs.erase(h->graphs.begin());
+            if (h->graphs.size() >= kMaxGraphs) {       // evict the least recently used batch size
+                size_t lru = 0;
+                for (size_t i = 1; i < h->graphs.size(); ++i)
+                    if (h->graphs[i].last_used < h->graphs[lru].last_used) lru = i;
+                cudaGraphExecDestroy(h->graphs[lru].exec);
+                h->graphs.erase(h->graphs.begin() + (long)lru);
             }
-            h->graphs.push_back(GraphEntry{B, audio, out, exec, s.n});
+            h->graphs.push_back(GraphEntry{B, exec, s.n, 0});
             ge = &h->graphs.back();
         }
+        ge->last_used = ++h->tick;
         CK(h, cudaGraphLaunch(ge->exec, st));
         h->launches = ge->launches;
     } else {
@@ -1175,8 +1197,8 @@ int vapb_profile_step(vapb_handle h, const float* audio, const int* ids, int B, 
     CK(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     CK(h, cudaStreamSynchronize(st));
-    memcpy(h->ids_pinned, ids, sizeof(int) * B);
-    CK(h, cudaMemcpyAsync(h->ids_dev, h->ids_pinned, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    memcpy(h->iobuf_pinned + sizeof(IoPtrs), ids, sizeof(int) * B);
+    CK(h, cudaMemcpyAsync(h->ids_dev, h->iobuf_pinned + sizeof(IoPtrs), sizeof(int) * B, cudaMemcpyHostToDevice, st));
     h->last_B = B;
     std::vector<std::pair<const char*, cudaEvent_t>> ev;
     Step s{h, st, B, audio, out};
