@@ -257,7 +257,6 @@ def run_ours(args):
     pool = min(n_chunks, 16)                                  # distinct input chunks cycled through
     Bg = world * B                                            # global streams; rank 0 is the ingest rank for N > 1
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    main = torch.cuda.current_stream(dev)
     step_i = 0
     if world == 1:
         audio_h = torch.from_numpy(make_audio(B, pool)).pin_memory()                  # [pool, B, 2, 1120]
@@ -454,12 +453,14 @@ def run_ours(args):
         }
         if dom and "us_per_launch" in dom:
             traffic, tsrc = None, None
-            tp = os.path.join(ROOT, "profiles", "r01_dominant_kernel.json")
+            tp = os.path.join(ROOT, "profiles", "r02_dominant_kernel.json")
+            if not os.path.exists(tp):
+                tp = os.path.join(ROOT, "profiles", "r01_dominant_kernel.json")
             if os.path.exists(tp):
                 tj = json.load(open(tp)).get(dom["kind"])
                 if tj:
                     traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
-                    tsrc = "profiles/r01_dominant_kernel.json (" + tj["source"] + ")"
+                    tsrc = "profiles/" + os.path.basename(tp) + " (" + tj["source"] + ")"
             if dom["kind"] == "stream":
                 fl = B * stream_kernel_gflop_per_frame(T) * 1e9
                 name = ("k_stream_tf: per-stream persistent transformer kernel (ring gather, ar_channel layer, vad, cross layers 0-1, "
@@ -507,13 +508,21 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-per-gpu", type=int, default=64)
-    ap.add_argument("--ctx-frames", type=int, default=50)
-    ap.add_argument("--head", default="vap", choices=["vap", "bc"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration: 2 = configs[1] (default, the one the metric is quoted on) ... 5 = configs[4]")
+    ap.add_argument("--batch-per-gpu", type=int, default=None, help="override the configuration's streams per GPU")
+    ap.add_argument("--ctx-frames", type=int, default=None, help="override the configuration's window T")
+    ap.add_argument("--head", default=None, choices=["vap", "bc"], help="override the configuration's head")
     ap.add_argument("--gemm", type=int, default=1, help="1 = tcgen05 bf16x3 GEMMs (product path), 0 = fp32 CUDA-core GEMMs")
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    custom = any(getattr(args, k) is not None and getattr(args, k) != cfg[k] for k in ("batch_per_gpu", "ctx_frames", "head"))
+    for k in ("batch_per_gpu", "ctx_frames", "head"):
+        if getattr(args, k) is None:
+            setattr(args, k, cfg[k])
+    args.label = cfg["label"] if not custom else "custom workload (not a BASELINE configuration)"
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
