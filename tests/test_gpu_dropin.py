@@ -127,3 +127,59 @@ def test_stateless_forward_matches_reference_static():
     print(f"stateless forward vs reference VAPRealTimeStatic: p/vad {worst_p:.2e}, embeddings {worst_e:.2e}")
     assert worst_p < 1e-4
     assert worst_e < 3e-4
+
+
+RATE_CASES = {      # fixture key -> (blob, head, frame_hz, T, columns)   tools/make_golden_rates.py
+    "jp_10hz_5000msec": ("vap_state_dict_jp_10hz_5000msec.vapw", "vap", 10, 50, 6),
+    "jp_5hz_3000msec": ("vap_state_dict_jp_5hz_3000msec.vapw", "vap", 5, 15, 6),
+    "jp_10hz_5000msec_MC": ("vap_state_dict_jp_10hz_5000msec_MC.vapw", "vap", 10, 50, 6),
+    "bc_erica_20hz_3000msec": ("vap-bc_state_dict_erica_20hz_3000msec.vapw", "bc", 20, 60, 2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RATE_CASES))
+def test_real_checkpoints_other_rates(name, fixture_audio):
+    """The shipped 10 Hz / 5 Hz / _MC / 3 s backchannel checkpoints on the CUDA path against outputs of the
+    reference itself (tests/golden/ref_rates.npz): downsample kernels of 10 / 20 taps (vap_main.py:203-212), LSTM
+    over 10 / 20 frames, T = 50 / 15 / 60."""
+    from vap_realtime_b200.engine import VapEngine
+    blob, head, hz, T, ncol = RATE_CASES[name]
+    audio, _ = fixture_audio
+    ref = np.load(os.path.join(GOLDEN, "ref_rates.npz"))["out_" + name]
+    eng = VapEngine(weights.load(built_asset(blob)), hz, T, max_streams=1, head=head)
+    eng.set_option("gemm", 1)
+    out = np.array([eng.step(torch.from_numpy(np.ascontiguousarray(chunk(audio, i, hz)))[None].cuda()).cpu().numpy()[0]
+                    for i in range(len(ref))])
+    d = np.abs(out[:, :ncol] - ref).max()
+    print(f"{name}: max|d| vs reference = {d:.2e}")
+    assert d < 1e-4
+
+
+@pytest.mark.parametrize("mode,hz,ctx,key", [("bc", 20, 3.0, "bc_erica_20hz_3000msec"), ("vap_MC", 10, 5.0, "jp_10hz_5000msec_MC")])
+def test_vap_queue_api_other_modes(fixture_audio, mode, hz, ctx, key):
+    """vap_realtime.Vap(mode='bc' | 'vap_MC') through start_process() / get_result() (vap_realtime/model.py:22-260).
+    The worker feeds 160-sample blocks and starts from 320 zeros, so the expected values come from the oracle on the
+    zero-prefixed audio (the oracle itself is pinned to the reference on these checkpoints: test_oracle_golden.py)."""
+    from vap_realtime_b200 import Vap, VapInput
+    blob, head, _, T, ncol = RATE_CASES[key]
+    audio, _ = fixture_audio
+    shift = 16000 // hz
+    n = 24
+    a = audio[:, : shift * n].astype(np.float64)
+    vap = Vap(mode=mode, frame_rate=hz, context_len_sec=ctx, mic1=VapInput.Array(a[0]), mic2=VapInput.Array(a[1]), device="cuda")
+    assert vap.audio_frame_size == shift + 320 and vap.audio_context_len == T
+    vap.start_process()
+    oracle = VapOracle(weights.load(built_asset(blob)), hz, T, head)
+    st = OracleState(1)
+    x = np.concatenate([np.zeros((2, 320)), a], axis=1).astype(np.float32)
+    for k in range(n - 1):
+        r = vap.get_result()
+        want = oracle.step(x[None, :, shift * k: shift * k + shift + 320], st).numpy()[0]
+        if mode == "bc":
+            assert set(r) == {"t", "x1", "x2", "p_bc_react", "p_bc_emo"}
+            got = np.array(r["p_bc_react"] + r["p_bc_emo"])
+        else:
+            assert set(r) == {"t", "x1", "x2", "p_now", "p_future", "vad"}
+            got = np.array(r["p_now"] + r["p_future"] + r["vad"])
+        assert np.abs(got - want[:ncol]).max() < 1e-4
+        assert len(r["x1"]) == shift

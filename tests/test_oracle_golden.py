@@ -70,6 +70,27 @@ def test_reference_fixture_bc(bc_weights, fixture_audio):
     assert np.all(out[:, 2:] == 0)
 
 
+RATE_CASES = {      # fixture key -> (blob, head, frame_hz, T, columns)   tools/make_golden_rates.py
+    "jp_10hz_5000msec": ("vap_state_dict_jp_10hz_5000msec.vapw", "vap", 10, 50, 6),
+    "jp_5hz_3000msec": ("vap_state_dict_jp_5hz_3000msec.vapw", "vap", 5, 15, 6),
+    "jp_10hz_5000msec_MC": ("vap_state_dict_jp_10hz_5000msec_MC.vapw", "vap", 10, 50, 6),
+    "bc_erica_20hz_3000msec": ("vap-bc_state_dict_erica_20hz_3000msec.vapw", "bc", 20, 60, 2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RATE_CASES))
+def test_reference_fixture_other_rates(name, fixture_audio):
+    """Real 10 Hz / 5 Hz / multi-condition / 3 s backchannel checkpoints against outputs of the reference itself."""
+    from vap_realtime_b200 import weights
+    blob, head, hz, T, ncol = RATE_CASES[name]
+    audio, _ = fixture_audio
+    ref = np.load(os.path.join(GOLDEN, "ref_rates.npz"))["out_" + name]
+    o = VapOracle(weights.load(built_asset(blob)), hz, T, head)
+    st = OracleState(1)
+    out = np.array([o.step(chunk(audio, i, hz)[None], st).numpy()[0] for i in range(len(ref))])
+    assert np.abs(out[:, :ncol] - ref).max() < TOL
+
+
 def test_batched_equals_single(vap_weights, fixture_audio):
     """Streams are independent: a batch of 3 equals 3 single-stream runs."""
     audio, _ = fixture_audio

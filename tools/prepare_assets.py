@@ -10,6 +10,8 @@ not exist.  No reference source code is read or copied.
 
   vap_jp_20hz_2500msec.vapw        jp_20hz_2500msec VAP + CPC weights (VAPW blob)
   vap_bc_erica_20hz_5000msec.vapw  backchannel model (config 5)
+  vap_state_dict_jp_{10hz_5000msec,5hz_3000msec,10hz_5000msec_MC}.vapw, vap-bc_state_dict_erica_20hz_3000msec.vapw
+                                   10 Hz / 5 Hz / multi-condition / 3 s backchannel checkpoints
   jpn_pair_16k.npz                 int16 L/R of jpn_inoue / jpn_sumida (golden input)
   golden_offline.npy               rvap/vap_main/output_offline.txt as float64 [5312, 5]
 """
@@ -29,6 +31,12 @@ OUT = os.path.join(ROOT, "assets", "_built")
 CHECKPOINTS = {
     "vap_jp_20hz_2500msec.vapw": "asset/vap/vap_state_dict_jp_20hz_2500msec.pt",
     "vap_bc_erica_20hz_5000msec.vapw": "asset/vap_bc/vap-bc_state_dict_erica_20hz_5000msec.pt",
+    # the other rates / modes pinned by tests/golden/ref_rates.npz (tools/make_golden_rates.py); named like the reference's
+    # files so that vap_realtime_b200.model._find_weights resolves them the way load_vap_model names them
+    "vap_state_dict_jp_10hz_5000msec.vapw": "asset/vap/vap_state_dict_jp_10hz_5000msec.pt",
+    "vap_state_dict_jp_5hz_3000msec.vapw": "asset/vap/vap_state_dict_jp_5hz_3000msec.pt",
+    "vap_state_dict_jp_10hz_5000msec_MC.vapw": "asset/vap/vap_state_dict_jp_10hz_5000msec_MC.pt",
+    "vap-bc_state_dict_erica_20hz_3000msec.vapw": "asset/vap_bc/vap-bc_state_dict_erica_20hz_3000msec.pt",
 }
 CPC = "asset/cpc/60k_epoch4-d0f474de.pt"
 
