@@ -71,7 +71,7 @@ __device__ __forceinline__ void fwait(uint32_t bar, uint32_t parity, int tag, in
     if (mbar_try_wait(bar, parity)) return;
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++polls > 40000000u) fwait_fail(tag, oi, parity);      // each failed try_wait suspends the thread for a while: seconds
+        if (VAPB_WAIT_POLLS != 0u && ++polls > VAPB_WAIT_POLLS) fwait_fail(tag, oi, parity);      // each failed try_wait suspends the thread for a while: seconds
     }
 }
 

@@ -291,6 +291,10 @@ k_gemm_tc(const GemmArgs g, const __grid_constant__ CUtensorMap map_hi, const __
         float* tbuf = reinterpret_cast<float*>(base_ptr) + warp * (32 * kEpiPitch);
         mbar_wait(bar_accum, 0);
         tc_fence_after();
+        // The epilogue staging aliases A stage 0.  Every A store is ordered before this point through
+        // full[s] -> tcgen05.mma -> tcgen05.commit -> bar_accum; the named barrier below states the same ordering
+        // among the 8 producer / epilogue warps in a form compute-sanitizer's racecheck can follow (~50 cycles).
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
         if (dbg && tid == 0) dbg[2] = clock64();          // accumulator complete, epilogue starts
         const uint32_t tm_row = tmem_base + ((uint32_t)(quad * 32) << 16);
         GemmArgs ge = g;                                  // split-K: partial z goes to its own slab, bias only in slab 0

@@ -40,6 +40,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// VAPB_WAIT_POLLS: failed polls before a wait gives up (0 = wait forever; compute-sanitizer builds use 0 because the
+// instrumented producer warps are orders of magnitude slower than the polling warp).
+#ifndef VAPB_WAIT_POLLS
+#define VAPB_WAIT_POLLS 40000000u
+#endif
 // Bounded wait: a mis-programmed pipeline must fail loudly (trap -> launch failure), never hang the GPU.
 // The loop counts polls instead of reading the clock (CS2R shares the XU pipe with the bf16 conversions of the
 // producer warps) and the failure path is a noreturn call, so nothing is live across the printf.
@@ -52,7 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++polls > 40000000u) mbar_wait_fail();
+        if (VAPB_WAIT_POLLS != 0u && ++polls > VAPB_WAIT_POLLS) mbar_wait_fail();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

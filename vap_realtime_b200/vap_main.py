@@ -123,6 +123,10 @@ def proc_serv_out(list_socket_out, port_number=50008):
         while True:
             conn, addr = s.accept()
             print('[OUT] Connected by', addr)
+            # non-blocking like the reference (vap_main.py:348-349): a consumer that stops reading makes sendall raise
+            # instead of stalling the broadcaster, and is dropped there
+            conn.setblocking(False)
+            conn.settimeout(0)
             list_socket_out.append(conn)
             print('[OUT] Current client num = %d' % len(list_socket_out))
 
@@ -204,6 +208,10 @@ def proc_serv_out_dist(list_socket_out, vap, result_fn=_result_dict, pack_fn=uti
             except Exception:
                 print('[OUT] Disconnected')
                 list_socket_out.remove(conn)
+                try:
+                    conn.close()
+                except OSError:
+                    pass
 
 
 def main(argv=None):
