@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("VAPB_LIB_OUT") or os.path.join(HERE, "libvapb200.so")   # VAPB_LIB_OUT / VAPB_NVCC_EXTRA: kernel experiments
-SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "fused_tf.cu", "vapb_api.cu"]
+SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "fused_tf.cu", "fused_tf2.cu", "vapb_api.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -636,6 +636,10 @@ bool ensure_attr(std::string* err) {
 
 }  // namespace
 
+bool tc_encode_bf16_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err) {
+    return encode_plane(map, ptr, (int)rows, (int)cols, box_rows, err);
+}
+
 bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vector<void*>& allocs, std::string& err) {
     if (!W_dev) {
         err = "tc_prepare_weight: null weight";

@@ -43,6 +43,9 @@ struct TcWorkspace {
 bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vector<void*>& allocs, std::string& err);
 bool tc_prepare_workspace(TcWorkspace& ws, size_t max_a_elems, std::vector<void*>& allocs, std::string& err);
 
+// 2D tensor map over a row-major bf16 tensor [rows][cols] (cols contiguous): box {64 cols, box_rows}, 128 B swizzle.
+bool tc_encode_bf16_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err);
+
 int tc_pick_ksplit(int M, int N, int K, int max_split);
 
 // Enqueues the GEMM; returns the number of kernels launched.

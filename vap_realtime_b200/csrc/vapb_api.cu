@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "fused_tf.cuh"
+#include "fused_tf2.cuh"
 
 #include <cuda_runtime.h>
 
@@ -120,6 +121,19 @@ struct vapb_ctx {
     int n_fops = 0;
     long long* fused_clk = nullptr;  // optional clock64 stamps per op (option fused_dbg)
     int opt_fused = 1, opt_fused_dbg = 0;
+    // stream kernel v2 (fused_tf2.cu, T <= 64): LayerNorm-folded concatenated weights, activation planes, op list
+    struct V2Layer {
+        float *Wg1 = nullptr, *Wqc = nullptr, *W1s = nullptr;          // fp32 [N][256] device copies (sources of the planes)
+        float *s_g1 = nullptr, *c_g1 = nullptr, *s_qc = nullptr, *c_qc = nullptr, *s_1 = nullptr, *c_1 = nullptr;
+        int n_g1 = 0, nln_g1 = 0;
+        TcWeight g1, qc, w1;
+    } v2[4];
+    float *X2f = nullptr, *St2 = nullptr;
+    __nv_bfloat16 *X2h = nullptr, *X2l = nullptr, *G1h = nullptr, *G1l = nullptr, *O2h = nullptr, *O2l = nullptr, *Qc2h = nullptr,
+                  *Qc2l = nullptr, *H2h = nullptr, *H2l = nullptr;
+    F2Op* f2ops = nullptr;
+    int n_f2ops = 0;
+    int opt_fused_v = 2;             // 2 = stream kernel v2 where it applies (T <= 64), 1 = always the first-generation kernel
     const float* fused_ds_part = nullptr;      // downsample partials handed to the stream kernel (its gather op finishes the embedding)
     long long fused_ds_stride = 0;
     int fused_ds_nsplit = 0;
@@ -533,6 +547,179 @@ int build_fused_ops(vapb_ctx* c) {
     return 0;
 }
 
+
+// ---- stream kernel v2: LayerNorm folded into the weights (fused_tf2.cuh) -------------------
+// rows of `out` += W[n][k] * g[k] (g = LayerNorm gain or null); s[n] = sum_k W'[n][k]; c[n] = sum_k b[k] W[n][k]
+void v2_append(std::vector<float>& out, std::vector<float>& sv, std::vector<float>& cv, const HostTensor* W, const HostTensor* g,
+               const HostTensor* b) {
+    if (!W) return;
+    const size_t N = W->numel / kD;
+    for (size_t n = 0; n < N; ++n) {
+        double ssum = 0.0, csum = 0.0;
+        for (int k = 0; k < kD; ++k) {
+            const float w = W->data[n * kD + k];
+            const float ws = g ? w * g->data[k] : w;
+            out.push_back(ws);
+            ssum += ws;
+            if (b) csum += (double)b->data[k] * w;
+        }
+        if (g) {
+            sv.push_back((float)ssum);
+            cv.push_back((float)csum);
+        }
+    }
+}
+
+void build_v2_weights(Loader& ld, vapb_ctx* c) {
+    for (int l = 0; l < 4; ++l) {
+        const std::string p = l == 0 ? std::string("ar_channel.layers.0.") : "ar.layers." + std::to_string(l - 1) + ".";
+        vapb_ctx::V2Layer& v = c->v2[l];
+        const HostTensor* g_sa = ld.get(p + "ln_self_attn.weight", {256});
+        const HostTensor* b_sa = ld.get(p + "ln_self_attn.bias", {256});
+        std::vector<float> W, sv, cv;
+        if (l < 3) v2_append(W, sv, cv, ld.get(p + "mha.query.weight", {256, 256}), g_sa, b_sa);
+        v2_append(W, sv, cv, ld.get(p + "mha.key.weight", {256, 256}), g_sa, b_sa);
+        v2_append(W, sv, cv, ld.get(p + "mha.value.weight", {256, 256}), g_sa, b_sa);
+        v.nln_g1 = (int)sv.size();
+        if (l > 0) {
+            v2_append(W, sv, cv, ld.get(p + "mha_cross.key.weight", {256, 256}), nullptr, nullptr);
+            v2_append(W, sv, cv, ld.get(p + "mha_cross.value.weight", {256, 256}), nullptr, nullptr);
+        }
+        v.n_g1 = (int)(W.size() / kD);
+        v.Wg1 = ld.upload(W);
+        v.s_g1 = ld.upload(sv);
+        v.c_g1 = ld.upload(cv);
+        if (l > 0 && l < 3) {
+            std::vector<float> Wq, sq, cq;
+            v2_append(Wq, sq, cq, ld.get(p + "mha_cross.query.weight", {256, 256}), ld.get(p + "ln_src_attn.weight", {256}),
+                      ld.get(p + "ln_src_attn.bias", {256}));
+            v.Wqc = ld.upload(Wq);
+            v.s_qc = ld.upload(sq);
+            v.c_qc = ld.upload(cq);
+        }
+        if (l < 3) {
+            std::vector<float> W1, s1, c1;
+            v2_append(W1, s1, c1, ld.get(p + "ffnetwork.0.weight", {768, 256}), ld.get(p + "ln_ffnetwork.weight", {256}),
+                      ld.get(p + "ln_ffnetwork.bias", {256}));
+            v.W1s = ld.upload(W1);
+            v.s_1 = ld.upload(s1);
+            v.c_1 = ld.upload(c1);
+        }
+    }
+}
+
+int build_fused2(vapb_ctx* c) {
+    if (c->T > 64) return 0;                       // v2 covers the both-channels-in-one-tile geometry only
+    std::string err;
+    for (int l = 0; l < 4; ++l) {
+        vapb_ctx::V2Layer& v = c->v2[l];
+        bool ok = tc_prepare_weight(v.Wg1, v.n_g1, kD, v.g1, c->allocs, err);
+        if (ok && v.Wqc) ok = tc_prepare_weight(v.Wqc, kD, kD, v.qc, c->allocs, err);
+        if (ok && v.W1s) ok = tc_prepare_weight(v.W1s, kFF, kD, v.w1, c->allocs, err);
+        if (!ok) return fail(c, VAPB_ECUDA, "stream kernel v2 weights: %s", err.c_str());
+    }
+    const size_t R2 = (size_t)c->max_batch * 128;
+    int rc = 0;
+#define DA2(ptr, n) if (!rc) rc = dalloc(c, &(ptr), (n))
+    DA2(c->X2f, R2 * kD);
+    DA2(c->St2, R2 * 16);
+    DA2(c->X2h, R2 * kD);
+    DA2(c->X2l, R2 * kD);
+    DA2(c->G1h, R2 * 1280);
+    DA2(c->G1l, R2 * 1280);
+    DA2(c->O2h, R2 * kD);
+    DA2(c->O2l, R2 * kD);
+    DA2(c->Qc2h, R2 * kD);
+    DA2(c->Qc2l, R2 * kD);
+    DA2(c->H2h, R2 * kFF);
+    DA2(c->H2l, R2 * kFF);
+#undef DA2
+    if (rc) return rc;
+    struct Planes { CUtensorMap hi128, lo128, hi64, lo64; };
+    auto planes = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, size_t cols, Planes& m) {
+        return tc_encode_bf16_2d(&m.hi128, hi, R2, cols, 128, err) && tc_encode_bf16_2d(&m.lo128, lo, R2, cols, 128, err) &&
+               tc_encode_bf16_2d(&m.hi64, hi, R2, cols, 64, err) && tc_encode_bf16_2d(&m.lo64, lo, R2, cols, 64, err);
+    };
+    Planes mX, mG1, mO, mQc, mH;
+    if (!planes(c->X2h, c->X2l, kD, mX) || !planes(c->G1h, c->G1l, 1280, mG1) || !planes(c->O2h, c->O2l, kD, mO) ||
+        !planes(c->Qc2h, c->Qc2l, kD, mQc) || !planes(c->H2h, c->H2l, kFF, mH))
+        return fail(c, VAPB_ECUDA, "stream kernel v2 tensor maps: %s", err.c_str());
+
+    std::vector<F2Op> ops;
+    auto gemm = [&](const Planes& A, int K, const TcWeight& w, int N, int out_mode, int n_ln, const float* ls, const float* lc, int act,
+                    __nv_bfloat16* oh, __nv_bfloat16* ol, int ld_out, int cta_sync) {
+        F2Op o;
+        memset(&o, 0, sizeof o);
+        o.m[0] = A.hi128; o.m[1] = A.lo128; o.m[2] = w.map_hi[1]; o.m[3] = w.map_lo[1];
+        o.f.kind = F2_GEMM; o.f.K = K; o.f.N = N; o.f.out_mode = out_mode; o.f.n_ln = n_ln; o.f.ln_s = ls; o.f.ln_c = lc; o.f.act = act;
+        o.f.out_hi = oh; o.f.out_lo = ol; o.f.ld_out = ld_out; o.f.cta_sync = cta_sync;
+        ops.push_back(o);
+    };
+    auto attn = [&](const Planes& Q, int qcol, int kcol, int vcol, const float* slopes, int sibling) {
+        F2Op o;
+        memset(&o, 0, sizeof o);
+        o.m[0] = Q.hi128; o.m[1] = Q.lo128; o.m[2] = mG1.hi64; o.m[3] = mG1.lo64;
+        o.f.kind = F2_ATTN; o.f.qcol = qcol; o.f.kcol = kcol; o.f.vcol = vcol; o.f.slopes = slopes; o.f.sibling = sibling;
+        o.f.out_hi = c->O2h; o.f.out_lo = c->O2l; o.f.ld_out = kD;
+        ops.push_back(o);
+    };
+    {
+        F2Op o;
+        memset(&o, 0, sizeof o);
+        o.f.kind = F2_GATHER;
+        ops.push_back(o);
+    }
+    for (int l = 0; l < 3; ++l) {
+        const LayerWeights& lw = c->layers[l];
+        const vapb_ctx::V2Layer& v = c->v2[l];
+        // Q / K / V of the self attention (LayerNorm folded) [+ K / V of the cross attention from the raw rows]: one op
+        gemm(mX, kD, v.g1, v.n_g1, F2_OUT_PLANES, v.nln_g1, v.s_g1, v.c_g1, 0, c->G1h, c->G1l, 1280, 1);
+        if (l == 1 && c->head_kind == VAPB_HEAD_VAP) ops.back().f.side = F2_SIDE_VAD;      // reads the ar_channel output
+        attn(mG1, 0, 256, 512, lw.sa.slopes, 0);
+        gemm(mO, kD, lw.sa.tc_proj, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, kD, 0);
+        if (lw.cross) {
+            gemm(mX, kD, v.qc, kD, F2_OUT_PLANES, kD, v.s_qc, v.c_qc, 0, c->Qc2h, c->Qc2l, kD, 1);
+            attn(mQc, 0, 768, 1024, lw.slopes_c, 1);
+            gemm(mO, kD, lw.tc_proj_c, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, kD, 0);
+        }
+        gemm(mX, kD, v.w1, kFF, F2_OUT_PLANES, kFF, v.s_1, v.c_1, 1, c->H2h, c->H2l, kFF, 0);
+        gemm(mH, kFF, lw.tc_w2, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, kD, 0);
+    }
+    {   // pruned last layer: window-wide K / V (self: LayerNorm folded, cross: raw rows) as fp32 rows for the newest-frame tail
+        const vapb_ctx::V2Layer& v = c->v2[3];
+        gemm(mX, kD, v.g1, v.n_g1, F2_OUT_F32, v.nln_g1, v.s_g1, v.c_g1, 0, nullptr, nullptr, 512, 0);
+        ops.back().f.out_f = c->QKV;
+        ops.back().f.out_f2 = c->KVc;
+        ops.back().f.side = F2_SIDE_GATHER_LAST;
+    }
+    for (const F2Op& o : ops)
+        if (o.f.kind == F2_GEMM && ((o.f.N & 255) || (o.f.K != 256 && o.f.K != 768))) return fail(c, VAPB_EINVAL, "stream kernel v2: bad op shape");
+    c->n_f2ops = (int)ops.size();
+    void* d = nullptr;
+    if (cudaMalloc(&d, ops.size() * sizeof(F2Op)) != cudaSuccess) return fail(c, VAPB_ENOMEM, "cudaMalloc(v2 op list) failed");
+    c->allocs.push_back(d);
+    if (cudaMemcpy(d, ops.data(), ops.size() * sizeof(F2Op), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(c, VAPB_ECUDA, "cudaMemcpy(v2 op list) failed");
+    c->f2ops = static_cast<F2Op*>(d);
+    if (!fused2_prepare(err)) return fail(c, VAPB_ECUDA, "%s", err.c_str());
+    return 0;
+}
+
+void fused_transformer2(Step& s) {
+    vapb_ctx* c = s.c;
+    Fused2Params p;
+    memset(&p, 0, sizeof p);
+    p.ops = c->f2ops; p.n_ops = c->n_f2ops; p.T = c->T;
+    p.ring = c->ring; p.ring_w = c->ring; p.count = c->count; p.ids = c->ids_dev; p.tvalid = c->tvalid;
+    p.ds_part = c->fused_ds_part; p.ds_stride = c->fused_ds_stride; p.ds_nsplit = c->fused_ds_nsplit;
+    p.ds_lnw = c->ds_lnw; p.ds_lnb = c->ds_lnb; p.e_out = c->ebuf;
+    p.Xf = c->X2f; p.Xh = c->X2h; p.Xl = c->X2l; p.stats = c->St2; p.Xlast = c->Xl;
+    p.va_w = c->va_w; p.va_b = c->va_b; p.out = s.out; p.io = s.io;
+    p.dbg = c->opt_fused_dbg ? c->fused_clk : nullptr;
+    launch_fused_tf2(p, s.B, s.st);
+    mark(s, "fused_tf");
+}
+
 void fused_transformer(Step& s) {
     vapb_ctx* c = s.c;
     FusedParams p;
@@ -632,7 +819,8 @@ void enqueue_step(Step& s) {
     if (use_stream) {
         // ---- ring gather, ar_channel, vad, cross layers 0-1 and the K/V of the pruned last layer: ONE launch,
         //      a cluster of two CTAs per stream (fused_tf.cu); then the newest-frame tail of the last layer
-        fused_transformer(s);
+        if (c->opt_fused_v == 2 && c->f2ops) fused_transformer2(s);
+        else fused_transformer(s);
         transformer_layer_last(s, c->layers[3], true);
     } else {
     // ---- window of the last T embeddings, oldest first (vap_main.py:274-283)
@@ -786,6 +974,7 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         c->Wh = ld.up("bc_head.weight", {3, 256});
         c->bh = ld.up("bc_head.bias", {3});
     }
+    build_v2_weights(ld, c);
     if (!ld.ok) FAIL_CREATE(VAPB_EWEIGHTS, "%s", ld.err.c_str());
 
     // ---- state + workspaces
@@ -869,6 +1058,7 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     }
 
     if (build_fused_ops(c) != 0) FAIL_CREATE(VAPB_ECUDA, "%s", c->err.c_str());
+    if (build_fused2(c) != 0) FAIL_CREATE(VAPB_ECUDA, "%s", c->err.c_str());
 
     // taps (allocated lazily when keep_taps is switched on)
     if (cudaDeviceSynchronize() != cudaSuccess) FAIL_CREATE(VAPB_ECUDA, "device error during create: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1071,7 +1261,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -1089,6 +1279,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "cluster2") h->tcws.cluster2 = value ? 1 : 0;
         else if (k == "fused") h->opt_fused = value;      // 0 off, 1 auto (one wave of clusters), 2 always
         else if (k == "fused_dbg") h->opt_fused_dbg = value;
+        else if (k == "fused_v") h->opt_fused_v = value == 1 ? 1 : 2;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -1125,6 +1316,7 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "cluster2") *value = h->tcws.cluster2;
     else if (k == "fused") *value = h->opt_fused;
     else if (k == "fused_dbg") *value = h->opt_fused_dbg;
+    else if (k == "fused_v") *value = (h->opt_fused_v == 2 && h->f2ops) ? 2 : 1;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
     return VAPB_OK;
@@ -1156,8 +1348,9 @@ int vapb_debug_tensor(vapb_handle h, const char* name, float* host_out, size_t c
         // clock64 deltas (cycles) per op of the stream kernel, cluster 0 / CTA 0 (option fused_dbg)
         std::vector<long long> clk(64);
         CK(h, cudaMemcpy(clk.data(), h->fused_clk, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
-        tmp.resize((size_t)h->n_fops);
-        for (int i = 0; i < h->n_fops; ++i) tmp[i] = (float)(clk[i + 1] - clk[i]);
+        const int nops = (h->opt_fused_v == 2 && h->f2ops) ? h->n_f2ops : h->n_fops;
+        tmp.resize((size_t)nops);
+        for (int i = 0; i < nops; ++i) tmp[i] = (float)(clk[i + 1] - clk[i]);
         for (int i = 1; i < 13; ++i) tmp.push_back(clk[40 + i] ? (float)(clk[40 + i] - clk[40]) : 0.f);   // fine stamps of op fused_dbg - 1
         n = tmp.size();
     } else if (k == "lstm_out") { src = h->Y; n = (size_t)NC * h->n_lstm * kD; }
