@@ -41,6 +41,11 @@ for n, c in zip(names, clk):
 fine = clk[len(names):]
 clk = clk[:len(names)]
 labels = ["A loaded(+LN) | att: Q loaded", "A stored | att: staged", "first acc_full | att: S done", "last acc_full | att: P written", "epilogue done | att: O written", "barrier passed", "mma: A kb0 ready | att: O done", "mma: first W ready", "mma: last issue", "tma: first issue", "tma: last issue", "A loads landed (before LN)"]
+if V == 2:
+    l2 = ["first acc_full", "last acc_full", "epilogue done (warp 0)", "barrier passed", "mma: first operands ready", "mma: last issue", "tma: first issue", "tma: last issue"]
+    print(f"fine stamps of op {DBG_OP} ({names[DBG_OP]}), cycles since op start:")
+    for l, v in zip(l2, fine):
+        print(f"   {l:30s} {v:9.0f}")
 if V == 1:
     print(f"fine stamps of op {DBG_OP} ({names[DBG_OP]}), cycles since op start:")
     for l, v in zip(labels, fine):

@@ -55,6 +55,7 @@ __device__ __forceinline__ void f2wait(uint32_t bar, uint32_t parity, int tag, i
 }
 
 struct Ctx2 {
+    long long* fine;       // fine clock stamps of one op (cluster 0 / CTA 0 only), else null
     uint32_t sbase, bars, tmem_base;
     F2Fields* opslot;
     int tid, warp, lane;
@@ -90,16 +91,46 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 256-bit global accesses (sm_100): a thread-per-row access touches one 128 B line per lane, and the LSU pays per line
+// visited, so fewer, wider instructions are what counts here
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* a) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]),
+                 "r"(a[5]), "r"(a[6]), "r"(a[7])
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_v8f(float* p, const float* a) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]),
+                 "f"(a[5]), "f"(a[6]), "f"(a[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_cg_v8f(const float* p, float* a) {
+    asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7])
+                 : "l"(p));
+}
+#ifdef VAPB_F2_NOSTORE        // timing experiment only: results are wrong
+#define F2_STORE(x)
+#else
+#define F2_STORE(x) x
+#endif
+
 // 32 consecutive fp32 values of one row -> 64 bytes in the hi plane and 64 bytes in the lo plane
 __device__ __forceinline__ void store_planes32(const float (&v)[32], __nv_bfloat16* hi, __nv_bfloat16* lo) {
     uint32_t h[16], l[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
+#ifdef VAPB_F2_V4
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
-        st_global_v4(hi + 8 * q4, h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
-        st_global_v4(lo + 8 * q4, l[4 * q4], l[4 * q4 + 1], l[4 * q4 + 2], l[4 * q4 + 3]);
+        F2_STORE(st_global_v4(hi + 8 * q4, h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);)
+        F2_STORE(st_global_v4(lo + 8 * q4, l[4 * q4], l[4 * q4 + 1], l[4 * q4 + 2], l[4 * q4 + 3]);)
     }
+#else
+    F2_STORE(st_global_v8(hi, h);)
+    F2_STORE(st_global_v8(hi + 16, h + 8);)
+    F2_STORE(st_global_v8(lo, l);)
+    F2_STORE(st_global_v8(lo + 16, l + 8);)
+#endif
 }
 // mean and M2 (sum of squared deviations) of 32 values, two passes in registers
 __device__ __forceinline__ float2 block_stats32(const float (&v)[32]) {
@@ -146,6 +177,7 @@ __device__ __forceinline__ void gemm_epilogue(const Ctx2& c, const F2Fields& op,
     float mu = 0.f, rstd = 1.f;
     if (op.n_ln > 0) row_stats(p.stats + grow * 16, mu, rstd);
     const int seq = row >> 6, pos = row & 63;
+    long long* fine = c.tid == 0 ? c.fine : nullptr;
     for (int s = 0; s < ns; ++s) {
         const int g = gs + s, slot = g & (kAcc - 1);
         const int n0 = 256 * s + 128 * c.r + 64 * hf;
@@ -155,16 +187,14 @@ __device__ __forceinline__ void gemm_epilogue(const Ctx2& c, const F2Fields& op,
             float v[32];
             float xr[32];
             if (op.out_mode == F2_OUT_X) {                 // residual rows requested before the accumulator is waited for
-                const float4* xp = reinterpret_cast<const float4*>(p.Xf + grow * kD + col);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float4 x4 = __ldcg(xp + e);
-                    xr[4 * e] = x4.x; xr[4 * e + 1] = x4.y; xr[4 * e + 2] = x4.z; xr[4 * e + 3] = x4.w;
-                }
+                for (int e = 0; e < 4; ++e) ld_global_cg_v8f(p.Xf + grow * kD + col + 8 * e, xr + 8 * e);
             }
             if (blk == 0) {
                 f2wait(c.acc_full(slot), (uint32_t)(g / kAcc) & 1u, 5, c.oi);
                 tc_fence_after();
+                if (fine && s == 0) fine[1] = clock64();            // first accumulator complete
+                if (fine && s == ns - 1) fine[2] = clock64();       // last accumulator complete
             }
             {
                 uint32_t raw[32];
@@ -198,9 +228,8 @@ __device__ __forceinline__ void gemm_epilogue(const Ctx2& c, const F2Fields& op,
             } else if (op.out_mode == F2_OUT_X) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] += xr[e];
-                float4* xo = reinterpret_cast<float4*>(p.Xf + grow * kD + col);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) xo[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                for (int e = 0; e < 4; ++e) { F2_STORE(st_global_v8f(p.Xf + grow * kD + col + 8 * e, v + 8 * e);) }
                 store_planes32(v, p.Xh + grow * kD + col, p.Xl + grow * kD + col);
                 const float2 st = block_stats32(v);
                 *reinterpret_cast<float2*>(p.stats + grow * 16 + (col >> 5) * 2) = st;
@@ -208,12 +237,12 @@ __device__ __forceinline__ void gemm_epilogue(const Ctx2& c, const F2Fields& op,
                 if (pos < c.T) {
                     float* dst = (col < 512 ? op.out_f : op.out_f2) + ((size_t)(2 * c.b + seq) * c.T + pos) * 512 + (col & 511);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        reinterpret_cast<float4*>(dst)[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                    for (int e = 0; e < 4; ++e) { F2_STORE(st_global_v8f(dst + 8 * e, v + 8 * e);) }
                 }
             }
         }
     }
+    if (fine) fine[3] = clock64();                                  // epilogue of warp 0 done
 }
 
 // ============================== GEMM: TMA side ==============================
@@ -225,6 +254,7 @@ __device__ __forceinline__ void gemm_tma(const Ctx2& c, const F2Op* gop, const F
     const bool resident = nkb <= kAStages;
     const int row0 = c.b * 128;
     int w = wt;
+    if (c.fine) c.fine[7] = clock64();                              // TMA: first issue
     for (int s = 0; s < ns; s += 2) {
         const int gsz = (s + 1 < ns) ? 2 : 1;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -246,6 +276,7 @@ __device__ __forceinline__ void gemm_tma(const Ctx2& c, const F2Op* gop, const F
             }
         }
     }
+    if (c.fine) c.fine[8] = clock64();                              // TMA: last issue
 }
 __device__ __forceinline__ int gemm_a_tiles(const F2Fields& op) {
     const int ns = op.N >> 8, nkb = op.K >> 6;
@@ -278,6 +309,7 @@ __device__ __forceinline__ void mma_group(const Ctx2& c, int nkb, bool resident,
             wb1 = wb0 + 64u * 128u;                      // rows 64..127 of the same W tile
         }
         tc_fence_after();
+        if (c.fine && first_group && kb == 0) c.fine[5] = clock64();     // MMA: first operands ready
         const uint32_t ab = c.a_stage(ast);
 #pragma unroll
         for (int k = 0; k < kBK / kUmmaK; ++k) {
@@ -316,6 +348,7 @@ __device__ __forceinline__ void gemm_mma(const Ctx2& c, const F2Fields& op, int 
         if (pair) mma_group<true>(c, nkb, resident, s == 0, last, at_group, w, slot0, slot1);
         else mma_group<false>(c, nkb, resident, s == 0, last, at_group, w, slot0, slot1);
     }
+    if (c.fine) c.fine[6] = clock64();                              // MMA: last issue
 }
 
 // ============================== attention (modules.py:82-110, 170-212) ==============================
@@ -619,6 +652,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
     c.b = blockIdx.x >> 1;
     c.T = p.T;
     c.oi = 0;
+    c.fine = nullptr;
     const int id = __ldg(p.ids + c.b);
     const int cnt = __ldg(p.count + id) + 1;           // frames including the one appended this step
     c.t = cnt < p.T ? cnt : p.T;
@@ -647,6 +681,8 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
         const int kind = __shfl_sync(0xffffffffu, op.kind, 0);
         const int cta_sync = __shfl_sync(0xffffffffu, op.cta_sync, 0);
         if (dbg) p.dbg[oi] = clock64();
+        c.fine = (p.dbg != nullptr && blockIdx.x == 0 && oi == p.dbg_op) ? p.dbg + 40 : nullptr;
+        if (c.fine && c.tid == 0) c.fine[0] = clock64();
         if (c.warp < kWorkers2) {
             if (kind == F2_GEMM) gemm_epilogue(c, op, p, gs);
             else if (kind == F2_ATTN) attn_workers(c, op, na);
@@ -693,6 +729,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
             na += 1;
         }
         op_sync(cta_sync);
+        if (c.fine && c.tid == 0) c.fine[4] = clock64();            // barrier passed
     }
     if (dbg) p.dbg[p.n_ops] = clock64();
     tc_fence_before();

@@ -84,7 +84,8 @@ struct Fused2Params {
     const float* va_b;
     float* out;
     const IoPtrs* io;
-    long long* dbg;          // optional clock64 stamps [n_ops + 1] of cluster 0 / CTA 0
+    long long* dbg;          // optional clock64 stamps [n_ops + 1] of cluster 0 / CTA 0; fine stamps of op dbg_op at [40..52)
+    int dbg_op;
 };
 
 size_t fused2_smem_bytes();

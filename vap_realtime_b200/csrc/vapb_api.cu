@@ -716,6 +716,7 @@ void fused_transformer2(Step& s) {
     p.Xf = c->X2f; p.Xh = c->X2h; p.Xl = c->X2l; p.stats = c->St2; p.Xlast = c->Xl;
     p.va_w = c->va_w; p.va_b = c->va_b; p.out = s.out; p.io = s.io;
     p.dbg = c->opt_fused_dbg ? c->fused_clk : nullptr;
+    p.dbg_op = c->opt_fused_dbg - 1;
     launch_fused_tf2(p, s.B, s.st);
     mark(s, "fused_tf");
 }
