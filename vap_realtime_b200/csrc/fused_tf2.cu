@@ -3,10 +3,16 @@
 // CTA anatomy (384 threads, 1 CTA per SM, cluster of 2 CTAs per stream):
 //   warps 0-7  workers: GEMM epilogues (tcgen05.ld -> LayerNorm correction / GELU / residual -> bf16 hi / lo planes,
 //              thread-per-row, straight to global), softmax, ring gather
-//   warp 8     TMA producer: A / Q / K tiles into the 4 "A" stages, W / V tiles into the 3-stage W ring
+//   warp 8     TMA producer of the W tiles; weights are constants, so it runs AHEAD of the op barriers (throttled only by
+//              the ring): the first W tiles of an op are in shared memory before the barrier in front of it opens
 //   warp 9     TMEM owner + the single thread that issues tcgen05.mma
-//   warp 10    side tasks (vad, newest-frame gather); warp 11 completes the warpgroup
-// Every stage holds the hi and the lo plane of one 128 x 64 bf16 tile (2 x 16 KB, 128 B swizzle).
+//   warp 10    TMA producer of everything that depends on the previous op: A tiles; Q / K / V tiles of the attention
+//   warp 11    side tasks (vad, newest-frame gather)
+// Every stage holds the hi and the lo plane of one 128 x 64 bf16 tile (2 x 16 KB, 128 B swizzle): an A ring (A tiles
+// stream once per subtile group; Q of the attention) and a W ring (W tiles; K and V of the attention at reserved ring
+// positions).  Each worker warp owns a 4 KB staging tile through which every global access of the epilogue is
+// transposed: tensor memory hands a thread one ROW, but a warp-wide access that touches 32 different 128 B lines costs
+// the LSU 32 passes (measured: thread-per-row stores made the first cut of this kernel slower than its predecessor).
 // All pipelines carry their phase across ops through running counters that every role advances identically.
 #include "fused_tf2.cuh"
 #include "tc_ptx.cuh"
@@ -24,8 +30,16 @@ constexpr int kWorkers2 = 8;
 constexpr int kThreads2 = (kWorkers2 + 4) * 32;
 constexpr int kPlane = 128 * kBK * 2;                 // one bf16 plane of a 128 x 64 tile: 16 KB
 constexpr int kStage = 2 * kPlane;                    // hi + lo
-constexpr int kAStages = 4, kWStg = 3, kAcc = 4;      // 4 accumulators of 128 columns = all of tensor memory
-constexpr int kSmem2 = (kAStages + kWStg) * kStage + 1024 /*alignment slack*/ + 512 /*barriers, op slots*/;
+#ifndef VAPB_F2_ASTAGES
+#define VAPB_F2_ASTAGES 2
+#endif
+#ifndef VAPB_F2_WSTAGES
+#define VAPB_F2_WSTAGES 4
+#endif
+constexpr int kAStages = VAPB_F2_ASTAGES, kWStg = VAPB_F2_WSTAGES, kAcc = 4;      // 4 accumulators of 128 columns = all of tensor memory
+constexpr int kStgBytes = 4096;                       // per worker warp: 32 rows x 128 bytes
+constexpr int kSmem2 = (kAStages + kWStg) * kStage + kWorkers2 * kStgBytes + 1024 /*alignment slack*/ + 512 /*barriers, op slots*/;
+static_assert(kAStages >= 2 && (kAStages % 2) == 0 && kWStg >= 3, "ring sizes");
 static_assert(kSmem2 <= 232448, "shared memory budget");
 
 __device__ __forceinline__ void cl_arrive2() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
@@ -63,16 +77,18 @@ struct Ctx2 {
     int T, t, oi;
     __device__ __forceinline__ uint32_t a_stage(int s) const { return sbase + (uint32_t)s * kStage; }
     __device__ __forceinline__ uint32_t w_stage(int s) const { return sbase + (uint32_t)(kAStages + s) * kStage; }
+    __device__ __forceinline__ uint32_t stg() const { return sbase + (uint32_t)(kAStages + kWStg) * kStage + (uint32_t)warp * kStgBytes; }
     __device__ __forceinline__ uint32_t a_full(int s) const { return bars + 8u * s; }
-    __device__ __forceinline__ uint32_t a_empty(int s) const { return bars + 32u + 8u * s; }
-    __device__ __forceinline__ uint32_t w_full(int s) const { return bars + 64u + 8u * s; }
-    __device__ __forceinline__ uint32_t w_empty(int s) const { return bars + 88u + 8u * s; }
-    __device__ __forceinline__ uint32_t acc_full(int s) const { return bars + 112u + 8u * s; }
-    __device__ __forceinline__ uint32_t acc_empty(int s) const { return bars + 144u + 8u * s; }
-    __device__ __forceinline__ uint32_t s_full() const { return bars + 176u; }
-    __device__ __forceinline__ uint32_t p_ready(int x) const { return bars + 184u + 8u * x; }
-    __device__ __forceinline__ uint32_t o_full(int x) const { return bars + 200u + 8u * x; }
-    __device__ __forceinline__ uint32_t tmem_slot() const { return bars + 216u; }
+    __device__ __forceinline__ uint32_t a_empty(int s) const { return bars + 8u * (kAStages + s); }
+    __device__ __forceinline__ uint32_t w_full(int s) const { return bars + 16u * kAStages + 8u * s; }
+    __device__ __forceinline__ uint32_t w_empty(int s) const { return bars + 16u * kAStages + 8u * (kWStg + s); }
+    __device__ __forceinline__ uint32_t misc() const { return bars + 16u * (kAStages + kWStg); }
+    __device__ __forceinline__ uint32_t acc_full(int s) const { return misc() + 8u * s; }
+    __device__ __forceinline__ uint32_t acc_empty(int s) const { return misc() + 32u + 8u * s; }
+    __device__ __forceinline__ uint32_t s_full() const { return misc() + 64u; }
+    __device__ __forceinline__ uint32_t p_ready(int x) const { return misc() + 72u + 8u * x; }
+    __device__ __forceinline__ uint32_t o_full(int x) const { return misc() + 88u + 8u * x; }
+    __device__ __forceinline__ uint32_t tmem_slot() const { return misc() + 104u; }
 };
 
 // exact-erf GELU, erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7), as in fused_tf.cu
@@ -91,46 +107,55 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// 256-bit global accesses (sm_100): a thread-per-row access touches one 128 B line per lane, and the LSU pays per line
-// visited, so fewer, wider instructions are what counts here
-__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* a) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]),
-                 "r"(a[5]), "r"(a[6]), "r"(a[7])
-                 : "memory");
-}
-__device__ __forceinline__ void st_global_v8f(float* p, const float* a) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]),
-                 "f"(a[5]), "f"(a[6]), "f"(a[7])
-                 : "memory");
-}
-__device__ __forceinline__ void ld_global_cg_v8f(const float* p, float* a) {
-    asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7])
-                 : "l"(p));
-}
 #ifdef VAPB_F2_NOSTORE        // timing experiment only: results are wrong
 #define F2_STORE(x)
 #else
 #define F2_STORE(x) x
 #endif
 
-// 32 consecutive fp32 values of one row -> 64 bytes in the hi plane and 64 bytes in the lo plane
-__device__ __forceinline__ void store_planes32(const float (&v)[32], __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    uint32_t h[16], l[16];
+// ---- per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by the row (conflict-free both ways) ----
+__device__ __forceinline__ uint32_t stg_addr(uint32_t stg, int row, int chunk) { return stg + (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4); }
+// thread-per-row side: lane = row, 32 words
+__device__ __forceinline__ void stg_put_row(uint32_t stg, int lane, const uint32_t* w) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], h[e], l[e]);
-#ifdef VAPB_F2_V4
+    for (int ch = 0; ch < 8; ++ch)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_addr(stg, lane, ch)), "r"(w[4 * ch]), "r"(w[4 * ch + 1]), "r"(w[4 * ch + 2]),
+                     "r"(w[4 * ch + 3])
+                     : "memory");
+}
+__device__ __forceinline__ void stg_get_row(uint32_t stg, int lane, uint32_t* w) {
 #pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-        F2_STORE(st_global_v4(hi + 8 * q4, h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);)
-        F2_STORE(st_global_v4(lo + 8 * q4, l[4 * q4], l[4 * q4 + 1], l[4 * q4 + 2], l[4 * q4 + 3]);)
+    for (int ch = 0; ch < 8; ++ch)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * ch]), "=r"(w[4 * ch + 1]), "=r"(w[4 * ch + 2]), "=r"(w[4 * ch + 3])
+                     : "r"(stg_addr(stg, lane, ch))
+                     : "memory");
+}
+// coalesced side: pass i covers rows 4i .. 4i + 3, 8 lanes x 16 bytes = the 128 bytes of one row
+__device__ __forceinline__ uint4 stg_get_co(uint32_t stg, int lane, int i) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(stg_addr(stg, 4 * i + (lane >> 3), lane & 7))
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg_put_co(uint32_t stg, int lane, int i, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_addr(stg, 4 * i + (lane >> 3), lane & 7)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+// staging tile -> 32 global rows of 128 bytes at `base + row * pitch` (bytes)
+__device__ __forceinline__ void stg_store_rows(uint32_t stg, int lane, uint8_t* base, size_t pitch) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 v = stg_get_co(stg, lane, i);
+        F2_STORE(st_global_v4(base + (size_t)(4 * i + (lane >> 3)) * pitch + (lane & 7) * 16, v.x, v.y, v.z, v.w);)
     }
-#else
-    F2_STORE(st_global_v8(hi, h);)
-    F2_STORE(st_global_v8(hi + 16, h + 8);)
-    F2_STORE(st_global_v8(lo, l);)
-    F2_STORE(st_global_v8(lo + 16, l + 8);)
-#endif
+}
+// a thread's 64 packed bf16 pairs (= 64 columns... 32 words = 128 bytes of one plane row) through the staging tile to global
+__device__ __forceinline__ void store_plane_rows(uint32_t stg, int lane, const uint32_t* w, __nv_bfloat16* base, size_t ld) {
+    stg_put_row(stg, lane, w);
+    __syncwarp();
+    stg_store_rows(stg, lane, reinterpret_cast<uint8_t*>(base), ld * 2);
+    __syncwarp();
 }
 // mean and M2 (sum of squared deviations) of 32 values, two passes in registers
 __device__ __forceinline__ float2 block_stats32(const float (&v)[32]) {
@@ -168,104 +193,209 @@ __device__ __forceinline__ void row_stats(const float* st_row, float& mu, float&
 }
 
 // ============================== GEMM: worker side (epilogue only) ==============================
-__device__ __forceinline__ void gemm_epilogue(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
+// Warp (q = warp & 3, hf = warp >> 2) drains columns [64 hf, 64 hf + 64) of every 128-column subtile for the 32 rows
+// of TMEM lane quadrant q.  Everything that goes to or comes from global memory passes through the warp's staging tile.
+__device__ __forceinline__ void ln_correct(float (&v)[32], const F2Fields& op, int col, float mu, float rstd) {
+    const float nm = -mu * rstd;
+#pragma unroll
+    for (int e4 = 0; e4 < 8; ++e4) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(op.ln_s + col) + e4);
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(op.ln_c + col) + e4);
+        v[4 * e4] = fmaf(rstd, v[4 * e4], fmaf(nm, s4.x, c4.x));
+        v[4 * e4 + 1] = fmaf(rstd, v[4 * e4 + 1], fmaf(nm, s4.y, c4.y));
+        v[4 * e4 + 2] = fmaf(rstd, v[4 * e4 + 2], fmaf(nm, s4.z, c4.z));
+        v[4 * e4 + 3] = fmaf(rstd, v[4 * e4 + 3], fmaf(nm, s4.w, c4.w));
+    }
+}
+
+// accumulator block (32 columns of this thread's row) -> registers; the warp's second block releases the accumulator
+__device__ __forceinline__ void load_acc_block(const Ctx2& c, uint32_t taddr, int slot, bool last, float (&v)[32]) {
+    uint32_t raw[32];
+    tmem_ld32(taddr, raw);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
+    if (last) {
+        tc_fence_before();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(c.acc_empty(slot));
+    }
+}
+
+// planes out (+ LayerNorm correction, + GELU): one 128-byte row per thread and plane through the staging tile
+__device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
     const int q = c.warp & 3, hf = c.warp >> 2;
-    const int row = 32 * q + c.lane;                       // tile row = TMEM lane
-    const size_t grow = (size_t)c.b * 128 + row;
+    const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
+    const size_t grow0 = (size_t)c.b * 128 + 32 * q;
     const int ns = op.N >> 8;
     const uint32_t tm_row = c.tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t stg = c.stg();
     float mu = 0.f, rstd = 1.f;
     if (op.n_ln > 0) row_stats(p.stats + grow * 16, mu, rstd);
-    const int seq = row >> 6, pos = row & 63;
     long long* fine = c.tid == 0 ? c.fine : nullptr;
     for (int s = 0; s < ns; ++s) {
         const int g = gs + s, slot = g & (kAcc - 1);
-        const int n0 = 256 * s + 128 * c.r + 64 * hf;
-#pragma unroll 1
+        const int col0 = 256 * s + 128 * c.r + 64 * hf;
+        f2wait(c.acc_full(slot), (uint32_t)(g / kAcc) & 1u, 5, c.oi);
+        tc_fence_after();
+        if (fine && s == 0) fine[1] = clock64();
+        if (fine && s == ns - 1) fine[2] = clock64();
+        uint32_t H[32], L[32];
+#pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-            const int col = n0 + 32 * blk;
+            const int col = col0 + 32 * blk;
             float v[32];
-            float xr[32];
-            if (op.out_mode == F2_OUT_X) {                 // residual rows requested before the accumulator is waited for
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ld_global_cg_v8f(p.Xf + grow * kD + col + 8 * e, xr + 8 * e);
-            }
-            if (blk == 0) {
-                f2wait(c.acc_full(slot), (uint32_t)(g / kAcc) & 1u, 5, c.oi);
-                tc_fence_after();
-                if (fine && s == 0) fine[1] = clock64();            // first accumulator complete
-                if (fine && s == ns - 1) fine[2] = clock64();       // last accumulator complete
-            }
-            {
-                uint32_t raw[32];
-                tmem_ld32(tm_row + (uint32_t)(slot * 128 + 64 * hf + 32 * blk), raw);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-            }
-            if (blk == 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (c.lane == 0) mbar_arrive(c.acc_empty(slot));
-            }
-            if (col < op.n_ln) {
-                const float nm = -mu * rstd;
-#pragma unroll
-                for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(op.ln_s + col) + e4);
-                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(op.ln_c + col) + e4);
-                    v[4 * e4] = fmaf(rstd, v[4 * e4], fmaf(nm, s4.x, c4.x));
-                    v[4 * e4 + 1] = fmaf(rstd, v[4 * e4 + 1], fmaf(nm, s4.y, c4.y));
-                    v[4 * e4 + 2] = fmaf(rstd, v[4 * e4 + 2], fmaf(nm, s4.z, c4.z));
-                    v[4 * e4 + 3] = fmaf(rstd, v[4 * e4 + 3], fmaf(nm, s4.w, c4.w));
-                }
-            }
+            load_acc_block(c, tm_row + (uint32_t)(slot * 128 + 64 * hf + 32 * blk), slot, blk == 1, v);
+            if (col < op.n_ln) ln_correct(v, op, col, mu, rstd);
             if (op.act == 1) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = gelu_as2(v[e]);
             }
-            if (op.out_mode == F2_OUT_PLANES) {
-                store_planes32(v, op.out_hi + grow * op.ld_out + col, op.out_lo + grow * op.ld_out + col);
-            } else if (op.out_mode == F2_OUT_X) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] += xr[e];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { F2_STORE(st_global_v8f(p.Xf + grow * kD + col + 8 * e, v + 8 * e);) }
-                store_planes32(v, p.Xh + grow * kD + col, p.Xl + grow * kD + col);
-                const float2 st = block_stats32(v);
-                *reinterpret_cast<float2*>(p.stats + grow * 16 + (col >> 5) * 2) = st;
-            } else {                                       // fp32 rows in the batched kernels' layout (tail of the pruned layer)
-                if (pos < c.T) {
-                    float* dst = (col < 512 ? op.out_f : op.out_f2) + ((size_t)(2 * c.b + seq) * c.T + pos) * 512 + (col & 511);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { F2_STORE(st_global_v8f(dst + 8 * e, v + 8 * e);) }
-                }
-            }
+            for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[16 * blk + e], L[16 * blk + e]);
         }
+        store_plane_rows(stg, c.lane, H, op.out_hi + grow0 * op.ld_out + col0, op.ld_out);
+        store_plane_rows(stg, c.lane, L, op.out_lo + grow0 * op.ld_out + col0, op.ld_out);
     }
-    if (fine) fine[3] = clock64();                                  // epilogue of warp 0 done
+    if (fine) fine[3] = clock64();
 }
 
-// ============================== GEMM: TMA side ==============================
-// Tile order = MMA order.  Subtiles go in groups: a PAIR of subtiles (two W tiles per k-block, two 128-column
-// accumulators issued interleaved) or a SINGLE subtile (one W tile per k-block, issued as two N = 64 halves).
-// K = 256: the four A tiles are loaded once and stay resident for every group; K = 768: A tiles stream with W.
-__device__ __forceinline__ void gemm_tma(const Ctx2& c, const F2Op* gop, const F2Fields& op, int at, int wt) {
-    const int ns = op.N >> 8, nkb = op.K >> 6;
-    const bool resident = nkb <= kAStages;
-    const int row0 = c.b * 128;
+// X update: x += acc (residual), fp32 rows + planes + LayerNorm block statistics.  The residual block is fetched coalesced
+// one block ahead and passes through the staging tile to reach the thread that owns the row.
+__device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
+    const int q = c.warp & 3, hf = c.warp >> 2;
+    const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
+    const size_t grow0 = (size_t)c.b * 128 + 32 * q;
+    const int ns = op.N >> 8;
+    const uint32_t tm_row = c.tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t stg = c.stg();
+    long long* fine = c.tid == 0 ? c.fine : nullptr;
+    auto res_ptr = [&](int col, int i) { return reinterpret_cast<const uint4*>(p.Xf + (grow0 + 4 * i + (c.lane >> 3)) * kD + col + 4 * (c.lane & 7)); };
+    for (int s = 0; s < ns; ++s) {
+        const int g = gs + s, slot = g & (kAcc - 1);
+        const int col0 = 256 * s + 128 * c.r + 64 * hf;
+        uint4 rc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rc[i] = __ldcg(res_ptr(col0, i));
+        f2wait(c.acc_full(slot), (uint32_t)(g / kAcc) & 1u, 5, c.oi);
+        tc_fence_after();
+        if (fine && s == 0) fine[1] = clock64();
+        if (fine && s == ns - 1) fine[2] = clock64();
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            const int col = col0 + 32 * blk;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) stg_put_co(stg, c.lane, i, rc[i]);
+            __syncwarp();
+            float v[32];
+            {
+                uint32_t xr[32];
+                stg_get_row(stg, c.lane, xr);
+                __syncwarp();
+                if (blk == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rc[i] = __ldcg(res_ptr(col0 + 32, i));       // next block's residual in flight
+                }
+                load_acc_block(c, tm_row + (uint32_t)(slot * 128 + 64 * hf + 32 * blk), slot, blk == 1, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] += __uint_as_float(xr[e]);
+            }
+            const float2 st = block_stats32(v);
+            F2_STORE(*reinterpret_cast<float2*>(p.stats + grow * 16 + (col >> 5) * 2) = st;)
+            {
+                uint32_t vb[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) vb[e] = __float_as_uint(v[e]);
+                stg_put_row(stg, c.lane, vb);
+            }
+            __syncwarp();
+            stg_store_rows(stg, c.lane, reinterpret_cast<uint8_t*>(p.Xf + grow0 * kD + col), kD * 4);
+            __syncwarp();
+            // planes of this block: 64 bytes hi | 64 bytes lo per row in one staging tile
+            {
+                uint32_t hl[32];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], hl[e], hl[16 + e]);
+                stg_put_row(stg, c.lane, hl);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // pass i: rows 4i .. 4i + 3; lanes 0-3 of a row's group carry hi, lanes 4-7 lo
+                const uint4 x4 = stg_get_co(stg, c.lane, i);
+                const int rr = 4 * i + (c.lane >> 3), ch = c.lane & 7;
+                __nv_bfloat16* dst = (ch < 4 ? p.Xh : p.Xl) + (grow0 + rr) * kD + col + 8 * (ch & 3);
+                F2_STORE(st_global_v4(dst, x4.x, x4.y, x4.z, x4.w);)
+            }
+            __syncwarp();
+        }
+    }
+    if (fine) fine[3] = clock64();
+}
+
+// fp32 rows in the batched kernels' layout (K / V of the pruned layer for the newest-frame tail)
+__device__ __noinline__ void epilogue_f32(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
+    const int q = c.warp & 3, hf = c.warp >> 2;
+    const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
+    const int ns = op.N >> 8;
+    const uint32_t tm_row = c.tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t stg = c.stg();
+    float mu = 0.f, rstd = 1.f;
+    if (op.n_ln > 0) row_stats(p.stats + grow * 16, mu, rstd);
+    long long* fine = c.tid == 0 ? c.fine : nullptr;
+    for (int s = 0; s < ns; ++s) {
+        const int g = gs + s, slot = g & (kAcc - 1);
+        const int col0 = 256 * s + 128 * c.r + 64 * hf;
+        f2wait(c.acc_full(slot), (uint32_t)(g / kAcc) & 1u, 5, c.oi);
+        tc_fence_after();
+        if (fine && s == 0) fine[1] = clock64();
+        if (fine && s == ns - 1) fine[2] = clock64();
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            const int col = col0 + 32 * blk;
+            float v[32];
+            load_acc_block(c, tm_row + (uint32_t)(slot * 128 + 64 * hf + 32 * blk), slot, blk == 1, v);
+            if (col < op.n_ln) ln_correct(v, op, col, mu, rstd);
+            uint32_t vb[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) vb[e] = __float_as_uint(v[e]);
+            stg_put_row(stg, c.lane, vb);
+            __syncwarp();
+            float* dst = (col < 512 ? op.out_f : op.out_f2) + (col & 511);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = 32 * q + 4 * i + (c.lane >> 3);
+                const int seq = rr >> 6, pos = rr & 63;
+                const uint4 x4 = stg_get_co(stg, c.lane, i);
+                if (pos < c.T) { F2_STORE(st_global_v4(dst + ((size_t)(2 * c.b + seq) * c.T + pos) * 512 + 4 * (c.lane & 7), x4.x, x4.y, x4.z, x4.w);) }
+            }
+            __syncwarp();
+        }
+    }
+    if (fine) fine[3] = clock64();
+}
+
+__device__ __forceinline__ void gemm_epilogue(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
+    const int mode = __shfl_sync(0xffffffffu, op.out_mode, 0);
+    if (mode == F2_OUT_PLANES) epilogue_planes(c, op, p, gs);
+    else if (mode == F2_OUT_X) epilogue_x(c, op, p, gs);
+    else epilogue_f32(c, op, p, gs);
+}
+
+// ============================== GEMM: tile schedule ==============================
+// Subtiles go in groups: a PAIR of subtiles (two W tiles per k-block, two 128-column accumulators issued interleaved)
+// or a SINGLE subtile (one W tile per k-block, issued as two N = 64 halves).  The A tiles stream once per group.
+__device__ __forceinline__ int gemm_groups(const F2Fields& op) { return ((op.N >> 8) + 1) >> 1; }
+__device__ __forceinline__ int gemm_a_tiles(const F2Fields& op) { return (op.K >> 6) * gemm_groups(op); }     // even (K/64 is 4 or 12)
+__device__ __forceinline__ int gemm_w_tiles(const F2Fields& op) { return (op.N >> 8) * (op.K >> 6); }
+
+// W tiles (warp 8, ahead of the op barriers)
+__device__ __forceinline__ void gemm_tma_w(const Ctx2& c, const F2Op* gop, int N, int K, int wt) {
+    const int ns = N >> 8, nkb = K >> 6;
     int w = wt;
-    if (c.fine) c.fine[7] = clock64();                              // TMA: first issue
+    if (c.fine) c.fine[7] = clock64();                              // W TMA: first issue
     for (int s = 0; s < ns; s += 2) {
         const int gsz = (s + 1 < ns) ? 2 : 1;
-        for (int kb = 0; kb < nkb; ++kb) {
-            if (s == 0 || !resident) {
-                const int ai = at + (resident ? kb : (s / 2) * nkb + kb);
-                const int st = ai % kAStages;
-                f2wait(c.a_empty(st), ((uint32_t)(ai / kAStages) & 1u) ^ 1u, 2, c.oi);
-                mbar_arrive_expect_tx(c.a_full(st), kStage);
-                tma_load_2d(c.a_stage(st), &gop->m[0], kb * kBK, row0, c.a_full(st));
-                tma_load_2d(c.a_stage(st) + kPlane, &gop->m[1], kb * kBK, row0, c.a_full(st));
-            }
+        for (int kb = 0; kb < nkb; ++kb)
             for (int u = 0; u < gsz; ++u, ++w) {
                 const int st = w % kWStg;
                 f2wait(c.w_empty(st), ((uint32_t)(w / kWStg) & 1u) ^ 1u, 4, c.oi);
@@ -273,30 +403,37 @@ __device__ __forceinline__ void gemm_tma(const Ctx2& c, const F2Op* gop, const F
                 const int n0 = 256 * (s + u) + 128 * c.r;
                 tma_load_2d(c.w_stage(st), &gop->m[2], kb * kBK, n0, c.w_full(st));
                 tma_load_2d(c.w_stage(st) + kPlane, &gop->m[3], kb * kBK, n0, c.w_full(st));
+#ifdef VAPB_F2_TRACE
+                if (blockIdx.x < 2 && c.oi < 3) printf("  W tile issued block %d op %d w %d stage %d n0 %d kb %d\n", blockIdx.x, c.oi, w, st, n0, kb);
+#endif
             }
-        }
     }
-    if (c.fine) c.fine[8] = clock64();                              // TMA: last issue
+    if (c.fine) c.fine[8] = clock64();                              // W TMA: last issue
 }
-__device__ __forceinline__ int gemm_a_tiles(const F2Fields& op) {
-    const int ns = op.N >> 8, nkb = op.K >> 6;
-    return nkb <= kAStages ? kAStages : nkb * ((ns + 1) / 2);       // always a multiple of kAStages (K = 768: 12 per group)
+// A tiles (warp 10, after the op barrier)
+__device__ __forceinline__ void gemm_tma_a(const Ctx2& c, const F2Op* gop, const F2Fields& op, int at) {
+    const int nkb = op.K >> 6, ng = gemm_groups(op);
+    const int row0 = c.b * 128;
+    int ai = at;
+    for (int gi = 0; gi < ng; ++gi)
+        for (int kb = 0; kb < nkb; ++kb, ++ai) {
+            const int st = ai % kAStages;
+            f2wait(c.a_empty(st), ((uint32_t)(ai / kAStages) & 1u) ^ 1u, 2, c.oi);
+            mbar_arrive_expect_tx(c.a_full(st), kStage);
+            tma_load_2d(c.a_stage(st), &gop->m[0], kb * kBK, row0, c.a_full(st));
+            tma_load_2d(c.a_stage(st) + kPlane, &gop->m[1], kb * kBK, row0, c.a_full(st));
+        }
 }
-__device__ __forceinline__ int gemm_w_tiles(const F2Fields& op) { return (op.N >> 8) * (op.K >> 6); }
 
 // ============================== GEMM: MMA side (one elected thread) ==============================
 template <bool PAIR>
-__device__ __forceinline__ void mma_group(const Ctx2& c, int nkb, bool resident, bool first_group, bool last_group, int at_group, int& w,
-                                          int slot0, int slot1) {
+__device__ __forceinline__ void mma_group(const Ctx2& c, int nkb, bool first_group, int& ai, int& w, int slot0, int slot1) {
     constexpr uint32_t idesc = PAIR ? make_idesc(128) : make_idesc(64);
     const uint32_t acc0 = c.tmem_base + (uint32_t)(slot0 * 128);
     const uint32_t acc1 = PAIR ? c.tmem_base + (uint32_t)(slot1 * 128) : acc0 + 64u;
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int ai = at_group + kb;
+    for (int kb = 0; kb < nkb; ++kb, ++ai) {
         const int ast = ai % kAStages;
-        if (first_group || !resident) {
-            f2wait(c.a_full(ast), (uint32_t)(ai / kAStages) & 1u, 1, c.oi);
-        }
+        f2wait(c.a_full(ast), (uint32_t)(ai / kAStages) & 1u, 1, c.oi);
         const int ws0 = w % kWStg;
         f2wait(c.w_full(ws0), (uint32_t)(w / kWStg) & 1u, 3, c.oi);
         uint32_t wb0 = c.w_stage(ws0), wb1;
@@ -325,7 +462,7 @@ __device__ __forceinline__ void mma_group(const Ctx2& c, int nkb, bool resident,
         }
         umma_commit(c.w_empty(ws0));
         if (PAIR) umma_commit(c.w_empty(ws1));
-        if (last_group || !resident) umma_commit(c.a_empty(ast));
+        umma_commit(c.a_empty(ast));
         w += PAIR ? 2 : 1;
     }
     umma_commit(c.acc_full(slot0));
@@ -334,8 +471,7 @@ __device__ __forceinline__ void mma_group(const Ctx2& c, int nkb, bool resident,
 
 __device__ __forceinline__ void gemm_mma(const Ctx2& c, const F2Fields& op, int at, int wt, int gs) {
     const int ns = op.N >> 8, nkb = op.K >> 6;
-    const bool resident = nkb <= kAStages;
-    int w = wt;
+    int w = wt, ai = at;
     for (int s = 0; s < ns; s += 2) {
         const bool pair = s + 1 < ns;
         const int g0 = gs + s, g1 = gs + s + 1;
@@ -343,19 +479,17 @@ __device__ __forceinline__ void gemm_mma(const Ctx2& c, const F2Fields& op, int 
         f2wait(c.acc_empty(slot0), ((uint32_t)(g0 / kAcc) & 1u) ^ 1u, 6, c.oi);
         if (pair) f2wait(c.acc_empty(slot1), ((uint32_t)(g1 / kAcc) & 1u) ^ 1u, 6, c.oi);
         tc_fence_after();
-        const int at_group = at + (resident ? 0 : (s / 2) * nkb);
-        const bool last = s + 2 >= ns;
-        if (pair) mma_group<true>(c, nkb, resident, s == 0, last, at_group, w, slot0, slot1);
-        else mma_group<false>(c, nkb, resident, s == 0, last, at_group, w, slot0, slot1);
+        if (pair) mma_group<true>(c, nkb, s == 0, ai, w, slot0, slot1);
+        else mma_group<false>(c, nkb, s == 0, ai, w, slot0, slot1);
     }
     if (c.fine) c.fine[6] = clock64();                              // MMA: last issue
 }
 
 // ============================== attention (modules.py:82-110, 170-212) ==============================
-// Two heads (2r, 2r + 1) per CTA.  Shared memory: Q of head x in A stage x, K of head x in A stage 2 + x, V of head x
-// in the next two W ring stages.  K / V tiles hold the keys of sequence c (or of its sibling for the cross attention)
-// in rows 64c .. 64c + 63, so row (c, i) of Q always finds its keys in columns 64c + j of S.
-// Tensor memory: S_x / P_x at columns 128x, O_x at 256 + 64x.
+// Two heads (2r, 2r + 1) per CTA.  Shared memory: Q of head x in the next two A ring stages; K of head x and V of head x
+// in the next four W ring positions (K0 K1 V0 V1; the W producer skips them, warp 10 fills them after the op barrier).
+// K / V tiles hold the keys of sequence c (or of its sibling for the cross attention) in rows 64c .. 64c + 63, so row
+// (c, i) of Q always finds its keys in columns 64c + j of S.  Tensor memory: S_x / P_x at columns 128x, O_x at 256 + 64x.
 constexpr uint32_t kTmS2 = 0, kTmO2 = 256;
 __host__ __device__ constexpr uint32_t make_idesc_bmn2(int bn) { return make_idesc(bn) | (1u << 16); }   // B operand MN-major
 
@@ -369,22 +503,11 @@ __device__ __forceinline__ void attn_tma(const Ctx2& c, const F2Op* gop, const F
         tma_load_2d(c.a_stage(st), &gop->m[0], col, row0, c.a_full(st));
         tma_load_2d(c.a_stage(st) + kPlane, &gop->m[1], col, row0, c.a_full(st));
     }
-    for (int x = 0; x < 2; ++x) {                          // K: two boxes of 64 rows (swapped for the sibling channel)
-        const int ai = at + 2 + x, st = ai % kAStages;
-        f2wait(c.a_empty(st), ((uint32_t)(ai / kAStages) & 1u) ^ 1u, 2, c.oi);
-        mbar_arrive_expect_tx(c.a_full(st), kStage);
-        const int col = op.kcol + (2 * c.r + x) * 64;
-        for (int half = 0; half < 2; ++half) {
-            const int src = row0 + 64 * (half ^ op.sibling);
-            tma_load_2d(c.a_stage(st) + half * (kPlane / 2), &gop->m[2], col, src, c.a_full(st));
-            tma_load_2d(c.a_stage(st) + kPlane + half * (kPlane / 2), &gop->m[3], col, src, c.a_full(st));
-        }
-    }
-    for (int x = 0; x < 2; ++x) {                          // V
-        const int w = wt + x, st = w % kWStg;
+    for (int i = 0; i < 4; ++i) {                          // K0 K1 V0 V1: two boxes of 64 rows each (swapped for the sibling channel)
+        const int w = wt + i, st = w % kWStg;
         f2wait(c.w_empty(st), ((uint32_t)(w / kWStg) & 1u) ^ 1u, 4, c.oi);
         mbar_arrive_expect_tx(c.w_full(st), kStage);
-        const int col = op.vcol + (2 * c.r + x) * 64;
+        const int col = (i < 2 ? op.kcol : op.vcol) + (2 * c.r + (i & 1)) * 64;
         for (int half = 0; half < 2; ++half) {
             const int src = row0 + 64 * (half ^ op.sibling);
             tma_load_2d(c.w_stage(st) + half * (kPlane / 2), &gop->m[2], col, src, c.w_full(st));
@@ -397,9 +520,10 @@ __device__ __forceinline__ void attn_mma(const Ctx2& c, int at, int wt, int na) 
     constexpr uint32_t idesc_s = make_idesc(128);
     constexpr uint32_t idesc_o = make_idesc_bmn2(64);
     const uint32_t par = (uint32_t)na & 1u;
-    for (int i = 0; i < 4; ++i) {
-        const int ai = at + i;
+    for (int x = 0; x < 2; ++x) {
+        const int ai = at + x, w = wt + x;
         f2wait(c.a_full(ai % kAStages), (uint32_t)(ai / kAStages) & 1u, 1, c.oi);
+        f2wait(c.w_full(w % kWStg), (uint32_t)(w / kWStg) & 1u, 3, c.oi);
     }
     tc_fence_after();
 #pragma unroll
@@ -409,7 +533,7 @@ __device__ __forceinline__ void attn_mma(const Ctx2& c, int at, int wt, int na) 
         for (int prod = 0; prod < 3; ++prod) {
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
-                const uint32_t qb = c.a_stage((at + x) % kAStages) + koff, kb = c.a_stage((at + 2 + x) % kAStages) + koff;
+                const uint32_t qb = c.a_stage((at + x) % kAStages) + koff, kb = c.w_stage((wt + x) % kWStg) + koff;
                 const uint32_t acc = c.tmem_base + kTmS2 + 128u * x;
                 if (prod == 0) umma_bf16(acc, make_desc(qb + kPlane), make_desc(kb), idesc_s, k ? 1u : 0u);
                 else if (prod == 1) umma_bf16(acc, make_desc(qb), make_desc(kb + kPlane), idesc_s, 1u);
@@ -418,11 +542,14 @@ __device__ __forceinline__ void attn_mma(const Ctx2& c, int at, int wt, int na) 
         }
     }
     umma_commit(c.s_full());
-    for (int i = 0; i < 4; ++i) umma_commit(c.a_empty((at + i) % kAStages));       // Q and K are free once S is complete
+    for (int x = 0; x < 2; ++x) {                           // Q and K are free once S is complete
+        umma_commit(c.a_empty((at + x) % kAStages));
+        umma_commit(c.w_empty((wt + x) % kWStg));
+    }
     f2wait(c.p_ready(0), par, 8, c.oi);
     f2wait(c.p_ready(1), par, 8, c.oi);
     for (int x = 0; x < 2; ++x) {
-        const int w = wt + x;
+        const int w = wt + 2 + x;
         f2wait(c.w_full(w % kWStg), (uint32_t)(w / kWStg) & 1u, 3, c.oi);
     }
     tc_fence_after();
@@ -434,7 +561,7 @@ __device__ __forceinline__ void attn_mma(const Ctx2& c, int at, int wt, int na) 
 #pragma unroll
             for (int x = 0; x < 2; ++x) {
                 const uint32_t acc = c.tmem_base + kTmO2 + 64u * x;
-                const uint32_t vh = c.w_stage((wt + x) % kWStg) + voff, vl = vh + kPlane;
+                const uint32_t vh = c.w_stage((wt + 2 + x) % kWStg) + voff, vl = vh + kPlane;
                 const uint32_t ph = c.tmem_base + kTmS2 + 128u * x + 32u * (kk >> 1) + 8u * (kk & 1), pl = ph + 16u;
                 if (prod == 0) umma_bf16_ta(acc, pl, make_desc(vh), idesc_o, kk ? 1u : 0u);
                 else if (prod == 1) umma_bf16_ta(acc, ph, make_desc(vl), idesc_o, 1u);
@@ -444,10 +571,10 @@ __device__ __forceinline__ void attn_mma(const Ctx2& c, int at, int wt, int na) 
     }
     umma_commit(c.o_full(0));
     umma_commit(c.o_full(1));
-    for (int x = 0; x < 2; ++x) umma_commit(c.w_empty((wt + x) % kWStg));
+    for (int x = 0; x < 2; ++x) umma_commit(c.w_empty((wt + 2 + x) % kWStg));
 }
 
-__device__ __forceinline__ void attn_workers(const Ctx2& c, const F2Fields& op, int na) {
+__device__ __noinline__ void attn_workers(const Ctx2& c, const F2Fields& op, int na) {
     const int q = c.warp & 3, x = c.warp >> 2;             // quadrant q of head x
     const uint32_t par = (uint32_t)na & 1u;
     const uint32_t tm_q = c.tmem_base + ((uint32_t)(q * 32) << 16);
@@ -507,56 +634,78 @@ __device__ __forceinline__ void attn_workers(const Ctx2& c, const F2Fields& op, 
     tc_fence_before();
     __syncwarp();
     if (c.lane == 0) mbar_arrive(c.p_ready(x));
-    // ---- O of head x, rows of quadrant q -> planes
+    // ---- O of head x, rows of quadrant q -> planes (64 columns = one 128-byte plane row per thread)
     f2wait(c.o_full(x), par, 9, c.oi);
     tc_fence_after();
-    const size_t grow = (size_t)c.b * 128 + row;
-#pragma unroll 1
+    uint32_t H[32], L[32];
+#pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t raw[32];
         tmem_ld32(tm_q + kTmO2 + 64u * x + 32u * half, raw);
-        float v[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-        const int col = head * 64 + 32 * half;
-        store_planes32(v, op.out_hi + grow * op.ld_out + col, op.out_lo + grow * op.ld_out + col);
+        for (int e = 0; e < 16; ++e) split2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1]), H[16 * half + e], L[16 * half + e]);
     }
     tc_fence_before();
+    const size_t grow0 = (size_t)c.b * 128 + 32 * q;
+    store_plane_rows(c.stg(), c.lane, H, op.out_hi + grow0 * op.ld_out + head * 64, op.ld_out);
+    store_plane_rows(c.stg(), c.lane, L, op.out_lo + grow0 * op.ld_out + head * 64, op.ld_out);
 }
 
 // ============================== ring gather (+ downsample tail) ==============================
-// Channel r of the stream: X rows 64r + j = ring rows oldest first (vap_main.py:274-283), zero rows above t; writes the
-// fp32 rows, their bf16 planes and the LayerNorm block statistics.  Warp 7 finishes the newest embedding first
-// (split-K sum of the downsample GEMM, LayerNorm, GELU: encoder_components.py:496-511) and appends it to the ring.
-__device__ __forceinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int id, int cnt) {
+// Channel r of the stream: X rows 64r + j = ring rows oldest first (vap_main.py:274-283), zero rows above t.  One warp per
+// row, a lane owns 8 consecutive floats: fp32 row, bf16 planes and the LayerNorm block statistics (4 lanes per block).
+__device__ __forceinline__ void emit_row(const Fused2Params& p, size_t grow, int lane, const float (&v8)[8]) {
+    *reinterpret_cast<float4*>(p.Xf + grow * kD + 8 * lane) = make_float4(v8[0], v8[1], v8[2], v8[3]);
+    *reinterpret_cast<float4*>(p.Xf + grow * kD + 8 * lane + 4) = make_float4(v8[4], v8[5], v8[6], v8[7]);
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2(v8[2 * e], v8[2 * e + 1], h[e], l[e]);
+    st_global_v4(p.Xh + grow * kD + 8 * lane, h[0], h[1], h[2], h[3]);
+    st_global_v4(p.Xl + grow * kD + 8 * lane, l[0], l[1], l[2], l[3]);
+    float bs = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bs += v8[i];
+    bs += __shfl_xor_sync(0xffffffffu, bs, 1);
+    bs += __shfl_xor_sync(0xffffffffu, bs, 2);
+    const float bm = bs * (1.0f / 32.0f);
+    float bq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float d = v8[i] - bm;
+        bq = fmaf(d, d, bq);
+    }
+    bq += __shfl_xor_sync(0xffffffffu, bq, 1);
+    bq += __shfl_xor_sync(0xffffffffu, bq, 2);
+    if ((lane & 3) == 0) *reinterpret_cast<float2*>(p.stats + grow * 16 + (lane >> 2) * 2) = make_float2(bm, bq);
+}
+
+__device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int id, int cnt) {
     const int ch = c.r;
     const float* rg = p.ring + ((size_t)id * 2 + ch) * p.T * kD;
     const size_t grow0 = (size_t)c.b * 128 + 64 * ch;
     const int jnew = p.ds_part ? c.t - 1 : -1;
-    for (int item = c.tid; item < 64 * 8; item += kWorkers2 * 32) {
-        const int j = item >> 3, blk = item & 7;
-        if (j == jnew) continue;
-        float v[32];
-        if (j < c.t) {
-            const int slot = (cnt - c.t + j) % p.T;
-            const float4* src = reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 32 * blk);
+    for (int j0 = c.warp; j0 < 64; j0 += 2 * kWorkers2) {          // two rows per pass: both loads in flight
+        float v[2][8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float4 x4 = __ldg(src + e);
-                v[4 * e] = x4.x; v[4 * e + 1] = x4.y; v[4 * e + 2] = x4.z; v[4 * e + 3] = x4.w;
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + u * kWorkers2;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+            if (j < c.t && j != jnew) {
+                const int slot = (cnt - c.t + j) % p.T;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane + 4));
+                v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
             }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = 0.f;
         }
-        const size_t grow = grow0 + j;
-        float4* xo = reinterpret_cast<float4*>(p.Xf + grow * kD + 32 * blk);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xo[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-        store_planes32(v, p.Xh + grow * kD + 32 * blk, p.Xl + grow * kD + 32 * blk);
-        *reinterpret_cast<float2*>(p.stats + grow * 16 + blk * 2) = block_stats32(v);
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + u * kWorkers2;
+            if (j != jnew) emit_row(p, grow0 + j, c.lane, v[u]);
+        }
     }
     if (p.ds_part && c.warp == kWorkers2 - 1) {
+        // newest embedding: split-K sum of the downsample GEMM, LayerNorm, exact GELU (encoder_components.py:496-511)
         const int n = 2 * c.b + ch;
         const float* pr = p.ds_part + (size_t)n * kD + 8 * c.lane;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
@@ -594,56 +743,34 @@ __device__ __forceinline__ void gather_op(const Ctx2& c, const Fused2Params& p, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) v8[i] = gelu_erf((v8[i] - mean) * rstd * ww[i] + bb[i]);
         const float4 o0 = make_float4(v8[0], v8[1], v8[2], v8[3]), o1 = make_float4(v8[4], v8[5], v8[6], v8[7]);
-        const size_t grow = grow0 + (c.t - 1);
-        float* dst[3] = {p.ring_w + (((size_t)id * 2 + ch) * p.T + (cnt - 1) % p.T) * kD, p.Xf + grow * kD, p.e_out ? p.e_out + (size_t)n * kD : nullptr};
+        float* dst[2] = {p.ring_w + (((size_t)id * 2 + ch) * p.T + (cnt - 1) % p.T) * kD, p.e_out ? p.e_out + (size_t)n * kD : nullptr};
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 2; ++k)
             if (dst[k]) {
                 *reinterpret_cast<float4*>(dst[k] + 8 * c.lane) = o0;
                 *reinterpret_cast<float4*>(dst[k] + 8 * c.lane + 4) = o1;
             }
-        // planes: 8 values = 16 bytes per plane; block statistics: 4 lanes share one 32-column block
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split2(v8[2 * e], v8[2 * e + 1], h[e], l[e]);
-        st_global_v4(p.Xh + grow * kD + 8 * c.lane, h[0], h[1], h[2], h[3]);
-        st_global_v4(p.Xl + grow * kD + 8 * c.lane, l[0], l[1], l[2], l[3]);
-        float bs = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bs += v8[i];
-        bs += __shfl_xor_sync(0xffffffffu, bs, 1);
-        bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-        const float bm = bs * (1.0f / 32.0f);
-        float bq = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float d = v8[i] - bm;
-            bq = fmaf(d, d, bq);
-        }
-        bq += __shfl_xor_sync(0xffffffffu, bq, 1);
-        bq += __shfl_xor_sync(0xffffffffu, bq, 2);
-        if ((c.lane & 3) == 0) *reinterpret_cast<float2*>(p.stats + grow * 16 + (c.lane >> 2) * 2) = make_float2(bm, bq);
+        emit_row(p, grow0 + (c.t - 1), c.lane, v8);
     }
     if (c.r == 0 && c.tid == 0) p.tvalid[c.b] = c.t;
 }
 
-// ============================== op loop, shared by every role ==============================
+// ============================== op loop ==============================
 __device__ __forceinline__ void op_sync(int cta_only) {
     fence_async_global();
     if (cta_only) {
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;" ::"n"(kThreads2) : "memory");
     } else {
         cl_arrive2();
         cl_wait2();
     }
 }
 
-// (No setmaxnreg here: the op loop is shared by every role and the epilogue fits the 168-register launch bound.)
 __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params p) {
     extern __shared__ uint8_t smem_raw[];
     Ctx2 c;
     c.sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    c.bars = c.sbase + (kAStages + kWStg) * kStage;
+    c.bars = c.sbase + (kAStages + kWStg) * kStage + kWorkers2 * kStgBytes;
     c.opslot = reinterpret_cast<F2Fields*>(smem_raw + (c.bars - smem_u32(smem_raw)) + 256);
     c.tid = threadIdx.x;
     c.warp = c.tid >> 5;
@@ -674,64 +801,105 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
 
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && c.tid == 0;
 
-    int at = 0, wt = 0, gs = 0, na = 0;      // running counters: A tiles, W tiles, accumulator subtiles, attentions
-    for (int oi = 0; oi < p.n_ops; ++oi) {
-        const F2Fields& op = c.opslot[oi & 1];
-        c.oi = oi;
-        const int kind = __shfl_sync(0xffffffffu, op.kind, 0);
-        const int cta_sync = __shfl_sync(0xffffffffu, op.cta_sync, 0);
-        if (dbg) p.dbg[oi] = clock64();
-        c.fine = (p.dbg != nullptr && blockIdx.x == 0 && oi == p.dbg_op) ? p.dbg + 40 : nullptr;
-        if (c.fine && c.tid == 0) c.fine[0] = clock64();
-        if (c.warp < kWorkers2) {
-            if (kind == F2_GEMM) gemm_epilogue(c, op, p, gs);
-            else if (kind == F2_ATTN) attn_workers(c, op, na);
-            else gather_op(c, p, id, cnt);
-        } else if (c.warp == kWorkers2) {
-            if (kind == F2_GEMM && elect_one()) gemm_tma(c, &p.ops[oi], op, at, wt);
-            if (kind == F2_ATTN && elect_one()) attn_tma(c, &p.ops[oi], op, at, wt);
-            __syncwarp();
-        } else if (c.warp == kWorkers2 + 1) {
-            if (oi + 1 < p.n_ops)        // fields of the next op -> the other shared-memory slot (visible after the op barrier)
-                reinterpret_cast<uint32_t*>(&c.opslot[(oi + 1) & 1])[c.lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ops[oi + 1].f) + c.lane);
-            if (kind == F2_GEMM && elect_one()) gemm_mma(c, op, at, wt, gs);
-            if (kind == F2_ATTN && elect_one()) attn_mma(c, at, wt, na);
-            __syncwarp();
-        } else if (c.warp == kWorkers2 + 2) {
-            const int side = __shfl_sync(0xffffffffu, op.side, 0);
-            if (side == F2_SIDE_VAD) {
-                // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
-                const float* xr = p.Xf + ((size_t)c.b * 128 + 64 * c.r + (c.t - 1)) * kD + 8 * c.lane;
-                const float4 x0 = __ldcg(reinterpret_cast<const float4*>(xr)), x1 = __ldcg(reinterpret_cast<const float4*>(xr + 4));
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane + 4));
-                float s = 0.f;
-                s = fmaf(x0.x, w0.x, s); s = fmaf(x0.y, w0.y, s); s = fmaf(x0.z, w0.z, s); s = fmaf(x0.w, w0.w, s);
-                s = fmaf(x1.x, w1.x, s); s = fmaf(x1.y, w1.y, s); s = fmaf(x1.z, w1.z, s); s = fmaf(x1.w, w1.w, s);
-                s = warp_sum2(s) + __ldg(p.va_b);
-                if (c.lane == 0) (p.io ? p.io->out : p.out)[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
-            } else if (side == F2_SIDE_GATHER_LAST) {
-                const float* xr = p.Xf + ((size_t)c.b * 128 + 64 * c.r + (c.t - 1)) * kD + 8 * c.lane;
-                float* xo = p.Xlast + (size_t)(2 * c.b + c.r) * kD + 8 * c.lane;
-                *reinterpret_cast<float4*>(xo) = __ldcg(reinterpret_cast<const float4*>(xr));
-                *reinterpret_cast<float4*>(xo + 4) = __ldcg(reinterpret_cast<const float4*>(xr + 4));
+    if (c.warp == kWorkers2) {
+        // ---------------- W producer: free-running, reads the op list from global memory ----------------
+        int wt = 0;
+        bool pending = false;                  // a cluster-barrier arrive of this warp is outstanding
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            c.oi = oi;
+            const F2Fields* gf = &p.ops[oi].f;
+            const int kind = __shfl_sync(0xffffffffu, __ldg(&gf->kind), 0);
+            const int N = __shfl_sync(0xffffffffu, __ldg(&gf->N), 0), K = __shfl_sync(0xffffffffu, __ldg(&gf->K), 0);
+            const int cta_sync = __shfl_sync(0xffffffffu, __ldg(&gf->cta_sync), 0);
+            c.fine = (p.dbg != nullptr && blockIdx.x == 0 && oi == p.dbg_op) ? p.dbg + 40 : nullptr;
+#ifdef VAPB_F2_TRACE
+            if (blockIdx.x < 2 && c.lane == 0 && oi < 4) printf("W-warp block %d op %d kind %d N %d K %d sync %d wt %d\n", blockIdx.x, oi, kind, N, K, cta_sync, wt);
+#endif
+            if (kind == F2_GEMM) {
+                if (elect_one()) gemm_tma_w(c, &p.ops[oi], N, K, wt);
+                wt += (N >> 8) * (K >> 6);
+            } else if (kind == F2_ATTN) {
+                // K0 K1 V0 V1 are filled by warp 10 at these four ring positions.  This warp still waits for them to be FREE, as
+                // if it filled them itself: a parity wait cannot tell "two phases behind" from "up to date", so a producer
+                // that skipped the wait could wrap around a stage whose previous tile has not been consumed yet.
+                for (int i = 0; i < 4; ++i) {
+                    const int w = wt + i;
+                    f2wait(c.w_empty(w % kWStg), ((uint32_t)(w / kWStg) & 1u) ^ 1u, 4, c.oi);
+                }
+                wt += 4;
             }
             __syncwarp();
+            // barrier behind op oi: arrive without waiting (the wait for the previous cluster barrier keeps this warp at most
+            // one cluster barrier ahead; CTA barriers are never adjacent in the op list)
+            if (cta_sync) {
+                asm volatile("bar.arrive 1, %0;" ::"n"(kThreads2) : "memory");      // named barrier 1 = the CTA-level op barrier
+            } else {
+                if (pending) cl_wait2();
+                cl_arrive2();
+                pending = true;
+            }
         }
-        // every role advances the running counters identically
-        if (kind == F2_GEMM) {
-            at += gemm_a_tiles(op);
-            wt += gemm_w_tiles(op);
-            gs += op.N >> 8;
-        } else if (kind == F2_ATTN) {
-            at += 4;
-            wt += 2;
-            na += 1;
+        if (pending) cl_wait2();
+    } else {
+        int at = 0, wt = 0, gs = 0, na = 0;      // running counters: A tiles, W tiles, accumulator subtiles, attentions
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            const F2Fields& op = c.opslot[oi & 1];
+            c.oi = oi;
+            const int kind = __shfl_sync(0xffffffffu, op.kind, 0);
+            const int cta_sync = __shfl_sync(0xffffffffu, op.cta_sync, 0);
+            if (dbg) p.dbg[oi] = clock64();
+            c.fine = (p.dbg != nullptr && blockIdx.x == 0 && oi == p.dbg_op) ? p.dbg + 40 : nullptr;
+            if (c.fine && c.tid == 0) c.fine[0] = clock64();
+            if (c.warp < kWorkers2) {
+                if (kind == F2_GEMM) gemm_epilogue(c, op, p, gs);
+                else if (kind == F2_ATTN) attn_workers(c, op, na);
+                else gather_op(c, p, id, cnt);
+            } else if (c.warp == kWorkers2 + 1) {
+                if (oi + 1 < p.n_ops)        // fields of the next op -> the other shared-memory slot (visible after the op barrier)
+                    reinterpret_cast<uint32_t*>(&c.opslot[(oi + 1) & 1])[c.lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ops[oi + 1].f) + c.lane);
+                if (kind == F2_GEMM && elect_one()) gemm_mma(c, op, at, wt, gs);
+                if (kind == F2_ATTN && elect_one()) attn_mma(c, at, wt, na);
+                __syncwarp();
+            } else if (c.warp == kWorkers2 + 2) {
+                if (kind == F2_GEMM && elect_one()) gemm_tma_a(c, &p.ops[oi], op, at);
+                if (kind == F2_ATTN && elect_one()) attn_tma(c, &p.ops[oi], op, at, wt);
+                __syncwarp();
+            } else {
+                const int side = __shfl_sync(0xffffffffu, op.side, 0);
+                if (side == F2_SIDE_VAD) {
+                    // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
+                    const float* xr = p.Xf + ((size_t)c.b * 128 + 64 * c.r + (c.t - 1)) * kD + 8 * c.lane;
+                    const float4 x0 = __ldcg(reinterpret_cast<const float4*>(xr)), x1 = __ldcg(reinterpret_cast<const float4*>(xr + 4));
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane));
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.va_w + 8 * c.lane + 4));
+                    float s = 0.f;
+                    s = fmaf(x0.x, w0.x, s); s = fmaf(x0.y, w0.y, s); s = fmaf(x0.z, w0.z, s); s = fmaf(x0.w, w0.w, s);
+                    s = fmaf(x1.x, w1.x, s); s = fmaf(x1.y, w1.y, s); s = fmaf(x1.z, w1.z, s); s = fmaf(x1.w, w1.w, s);
+                    s = warp_sum2(s) + __ldg(p.va_b);
+                    if (c.lane == 0) (p.io ? p.io->out : p.out)[c.b * 6 + 4 + c.r] = 1.0f / (1.0f + expf(-s));
+                } else if (side == F2_SIDE_GATHER_LAST) {
+                    const float* xr = p.Xf + ((size_t)c.b * 128 + 64 * c.r + (c.t - 1)) * kD + 8 * c.lane;
+                    float* xo = p.Xlast + (size_t)(2 * c.b + c.r) * kD + 8 * c.lane;
+                    *reinterpret_cast<float4*>(xo) = __ldcg(reinterpret_cast<const float4*>(xr));
+                    *reinterpret_cast<float4*>(xo + 4) = __ldcg(reinterpret_cast<const float4*>(xr + 4));
+                }
+                __syncwarp();
+            }
+            // every role advances the running counters identically
+            if (kind == F2_GEMM) {
+                at += gemm_a_tiles(op);
+                wt += gemm_w_tiles(op);
+                gs += op.N >> 8;
+            } else if (kind == F2_ATTN) {
+                at += 2;
+                wt += 4;
+                na += 1;
+            }
+            op_sync(cta_sync);
+            if (c.fine && c.tid == 0) c.fine[4] = clock64();            // barrier passed
         }
-        op_sync(cta_sync);
-        if (c.fine && c.tid == 0) c.fine[4] = clock64();            // barrier passed
+        if (dbg) p.dbg[p.n_ops] = clock64();
     }
-    if (dbg) p.dbg[p.n_ops] = clock64();
     tc_fence_before();
     __syncthreads();
     if (c.warp == kWorkers2 + 1) tmem_dealloc(c.tmem_base, 512u);
