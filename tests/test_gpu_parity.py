@@ -179,7 +179,7 @@ def test_option_variants_agree(vap_weights, fixture_audio):
     audio, ref = fixture_audio
     outs = {}
     for name, opts in {"default": {}, "lstm_unfused": {"lstm_fused": 0}, "tile64": {"tile_n": 64},
-                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}, "ln_unfused": {"fuse_ln": 0}, "no_k256": {"k256": 0}, "pdl": {"pdl": 1}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "no_fused": {"fused": 0}, "stream_v1": {"fused_v": 1}}.items():
+                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}, "ln_unfused": {"fuse_ln": 0}, "no_k256": {"k256": 0}, "pdl": {"pdl": 1}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "no_fused": {"fused": 0}, "stream_v2": {"fused_v": 2}}.items():
         eng = VapEngine(vap_weights, 20, 50, max_streams=3)
         eng.set_option("gemm", DEF)
         for k, v in opts.items():
@@ -277,8 +277,8 @@ def test_full_size_batch_invariance(vap_weights, T, B):
     assert worst_or < 1e-4
 
 
-@pytest.mark.parametrize("T", [3, 33, 64, 65, 100, 128])
-def test_stream_kernel_window_edges(T):
+@pytest.mark.parametrize("T,gen", [(3, 1), (33, 1), (64, 1), (65, 1), (100, 1), (128, 1), (3, 2), (33, 2), (50, 2), (64, 2)])
+def test_stream_kernel_window_edges(T, gen):
     """Per-stream persistent transformer kernel at the edges of its two tilings: 2T <= 128 rows per cluster
     (both channels in one M tile, N split over the two CTAs) up to T = 64, one channel per CTA from T = 65 to
     the maximum window of 128 frames.  Random weights, non-identity slots, warm-up (t < T) and sliding window;
@@ -291,8 +291,9 @@ def test_stream_kernel_window_edges(T):
     for e in (fused, plain):
         e.set_option("gemm", 1)
     fused.set_option("fused", 2)          # always (also the default here: 2B <= 148)
+    fused.set_option("fused_v", gen)      # generation of the stream kernel; the second one covers T <= 64
     plain.set_option("fused", 0)
-    assert fused.get_option("fused_v") == (2 if T <= 64 else 1)      # second-generation kernel up to T = 64
+    assert fused.get_option("fused_v") == gen
     slots = [6, 0, 3]
     audio = np.stack([synthetic_audio(20 + s, n_steps) for s in range(3)])
     st = OracleState(3)
@@ -305,7 +306,7 @@ def test_stream_kernel_window_edges(T):
         assert np.isfinite(x).all()
         worst_or = max(worst_or, np.abs(x - want).max())
         worst_ab = max(worst_ab, np.abs(x - y).max())
-    print(f"stream kernel T={T}: vs oracle {worst_or:.2e}, vs batched kernels {worst_ab:.2e}, {fused.last_launch_count} / {plain.last_launch_count} kernels")
+    print(f"stream kernel v{gen} T={T}: vs oracle {worst_or:.2e}, vs batched kernels {worst_ab:.2e}, {fused.last_launch_count} / {plain.last_launch_count} kernels")
     assert fused.last_launch_count < plain.last_launch_count
     assert worst_or < 1e-4
     assert worst_ab < 5e-5

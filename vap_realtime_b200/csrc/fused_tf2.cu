@@ -1,6 +1,13 @@
 // Per-stream persistent transformer kernel, second generation -- see fused_tf2.cuh for the scheme.
 //
-// CTA anatomy (384 threads, 1 CTA per SM, cluster of 2 CTAs per stream):
+// Cluster of FOUR CTAs = two streams x two column halves (rank k: stream slot k >> 1, half r = k & 1).  The kernel is bound
+// by the SM <-> L2 fabric (every CTA streams its half of every weight matrix for every stream), so both operand streams
+// are multicast: the two CTAs of a stream share every A tile (each issues 64 of its 128 rows to both), the two CTAs with
+// the same half r share every W tile across the two streams (each issues 64 of its 128 rows to both).  "Empty" barriers
+// therefore collect one tcgen05.commit from each of the two consumers.  An odd batch gets a ghost stream that runs the
+// same pipeline on scratch rows and writes no state.
+//
+// CTA anatomy (384 threads, 1 CTA per SM):
 //   warps 0-7  workers: GEMM epilogues (tcgen05.ld -> LayerNorm correction / GELU / residual -> bf16 hi / lo planes,
 //              thread-per-row, straight to global), softmax, ring gather
 //   warp 8     TMA producer of the W tiles; weights are constants, so it runs AHEAD of the op barriers (throttled only by
@@ -73,7 +80,9 @@ struct Ctx2 {
     uint32_t sbase, bars, tmem_base;
     F2Fields* opslot;
     int tid, warp, lane;
-    int b, r;              // stream index in the batch, CTA rank in the cluster
+    int b, r;              // stream index in the batch (= workspace slot), column half
+    int sidx, ghost;       // stream slot inside the cluster; ghost = padding stream of an odd batch (no state is written)
+    uint16_t mask_a, mask_w;   // multicast masks: the two CTAs of this stream / the two CTAs of this column half
     int T, t, oi;
     __device__ __forceinline__ uint32_t a_stage(int s) const { return sbase + (uint32_t)s * kStage; }
     __device__ __forceinline__ uint32_t w_stage(int s) const { return sbase + (uint32_t)(kAStages + s) * kStage; }
@@ -107,10 +116,17 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-#ifdef VAPB_F2_NOSTORE        // timing experiment only: results are wrong
+// timing experiments only (results are wrong): VAPB_F2_NOSTORE drops every epilogue store, _NOSTORE_P only the plane
+// stores, _NOSTORE_X only the fp32 stores; VAPB_F2_NOFENCE drops the proxy fence in front of the op barrier; VAPB_F2_NOGELU
+#if defined(VAPB_F2_NOSTORE) || defined(VAPB_F2_NOSTORE_X)
 #define F2_STORE(x)
 #else
 #define F2_STORE(x) x
+#endif
+#if defined(VAPB_F2_NOSTORE) || defined(VAPB_F2_NOSTORE_P)
+#define F2_STORE_P(x)
+#else
+#define F2_STORE_P(x) x
 #endif
 
 // ---- per-warp staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by the row (conflict-free both ways) ----
@@ -143,18 +159,20 @@ __device__ __forceinline__ void stg_put_co(uint32_t stg, int lane, int i, uint4 
                  : "memory");
 }
 // staging tile -> 32 global rows of 128 bytes at `base + row * pitch` (bytes)
+template <bool PLANE = false>
 __device__ __forceinline__ void stg_store_rows(uint32_t stg, int lane, uint8_t* base, size_t pitch) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const uint4 v = stg_get_co(stg, lane, i);
-        F2_STORE(st_global_v4(base + (size_t)(4 * i + (lane >> 3)) * pitch + (lane & 7) * 16, v.x, v.y, v.z, v.w);)
+        if (PLANE) { F2_STORE_P(st_global_v4(base + (size_t)(4 * i + (lane >> 3)) * pitch + (lane & 7) * 16, v.x, v.y, v.z, v.w);) }
+        else { F2_STORE(st_global_v4(base + (size_t)(4 * i + (lane >> 3)) * pitch + (lane & 7) * 16, v.x, v.y, v.z, v.w);) }
     }
 }
 // a thread's 64 packed bf16 pairs (= 64 columns... 32 words = 128 bytes of one plane row) through the staging tile to global
 __device__ __forceinline__ void store_plane_rows(uint32_t stg, int lane, const uint32_t* w, __nv_bfloat16* base, size_t ld) {
     stg_put_row(stg, lane, w);
     __syncwarp();
-    stg_store_rows(stg, lane, reinterpret_cast<uint8_t*>(base), ld * 2);
+    stg_store_rows<true>(stg, lane, reinterpret_cast<uint8_t*>(base), ld * 2);
     __syncwarp();
 }
 // mean and M2 (sum of squared deviations) of 32 values, two passes in registers
@@ -246,10 +264,9 @@ __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Fields& op, 
             float v[32];
             load_acc_block(c, tm_row + (uint32_t)(slot * 128 + 64 * hf + 32 * blk), slot, blk == 1, v);
             if (col < op.n_ln) ln_correct(v, op, col, mu, rstd);
-            if (op.act == 1) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = gelu_as2(v[e]);
-            }
+#ifndef VAPB_F2_NOGELU
+            if (op.act == 1) gelu_block(v);          // eight independent chains in flight (tc_ptx.cuh)
+#endif
 #pragma unroll
             for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[16 * blk + e], L[16 * blk + e]);
         }
@@ -324,7 +341,7 @@ __device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Fields& op, const
                 const uint4 x4 = stg_get_co(stg, c.lane, i);
                 const int rr = 4 * i + (c.lane >> 3), ch = c.lane & 7;
                 __nv_bfloat16* dst = (ch < 4 ? p.Xh : p.Xl) + (grow0 + rr) * kD + col + 8 * (ch & 3);
-                F2_STORE(st_global_v4(dst, x4.x, x4.y, x4.z, x4.w);)
+                F2_STORE_P(st_global_v4(dst, x4.x, x4.y, x4.z, x4.w);)
             }
             __syncwarp();
         }
@@ -366,7 +383,7 @@ __device__ __noinline__ void epilogue_f32(const Ctx2& c, const F2Fields& op, con
                 const int rr = 32 * q + 4 * i + (c.lane >> 3);
                 const int seq = rr >> 6, pos = rr & 63;
                 const uint4 x4 = stg_get_co(stg, c.lane, i);
-                if (pos < c.T) { F2_STORE(st_global_v4(dst + ((size_t)(2 * c.b + seq) * c.T + pos) * 512 + 4 * (c.lane & 7), x4.x, x4.y, x4.z, x4.w);) }
+                if (pos < c.T && !c.ghost) { F2_STORE(st_global_v4(dst + ((size_t)(2 * c.b + seq) * c.T + pos) * 512 + 4 * (c.lane & 7), x4.x, x4.y, x4.z, x4.w);) }
             }
             __syncwarp();
         }
@@ -400,9 +417,11 @@ __device__ __forceinline__ void gemm_tma_w(const Ctx2& c, const F2Op* gop, int N
                 const int st = w % kWStg;
                 f2wait(c.w_empty(st), ((uint32_t)(w / kWStg) & 1u) ^ 1u, 4, c.oi);
                 mbar_arrive_expect_tx(c.w_full(st), kStage);
-                const int n0 = 256 * (s + u) + 128 * c.r;
-                tma_load_2d(c.w_stage(st), &gop->m[2], kb * kBK, n0, c.w_full(st));
-                tma_load_2d(c.w_stage(st) + kPlane, &gop->m[3], kb * kBK, n0, c.w_full(st));
+                // this CTA's share of the tile: 64 of its 128 rows, delivered to both CTAs that compute column half r
+                const int n0 = 256 * (s + u) + 128 * c.r + 64 * c.sidx;
+                const uint32_t off = (uint32_t)c.sidx * (kPlane / 2);
+                tma_load_2d_mc(c.w_stage(st) + off, &gop->m[2], kb * kBK, n0, c.w_full(st), c.mask_w);
+                tma_load_2d_mc(c.w_stage(st) + kPlane + off, &gop->m[3], kb * kBK, n0, c.w_full(st), c.mask_w);
 #ifdef VAPB_F2_TRACE
                 if (blockIdx.x < 2 && c.oi < 3) printf("  W tile issued block %d op %d w %d stage %d n0 %d kb %d\n", blockIdx.x, c.oi, w, st, n0, kb);
 #endif
@@ -420,8 +439,10 @@ __device__ __forceinline__ void gemm_tma_a(const Ctx2& c, const F2Op* gop, const
             const int st = ai % kAStages;
             f2wait(c.a_empty(st), ((uint32_t)(ai / kAStages) & 1u) ^ 1u, 2, c.oi);
             mbar_arrive_expect_tx(c.a_full(st), kStage);
-            tma_load_2d(c.a_stage(st), &gop->m[0], kb * kBK, row0, c.a_full(st));
-            tma_load_2d(c.a_stage(st) + kPlane, &gop->m[1], kb * kBK, row0, c.a_full(st));
+            // this CTA's share: rows 64r .. 64r + 63 of the stream's tile, delivered to both CTAs of the stream
+            const uint32_t off = (uint32_t)c.r * (kPlane / 2);
+            tma_load_2d_mc(c.a_stage(st) + off, &gop->m[0], kb * kBK, row0 + 64 * c.r, c.a_full(st), c.mask_a);
+            tma_load_2d_mc(c.a_stage(st) + kPlane + off, &gop->m[1], kb * kBK, row0 + 64 * c.r, c.a_full(st), c.mask_a);
         }
 }
 
@@ -460,9 +481,9 @@ __device__ __forceinline__ void mma_group(const Ctx2& c, int nkb, bool first_gro
             umma_bf16(acc0, make_desc(ab + koff), make_desc(wb0 + koff), idesc, 1u);
             umma_bf16(acc1, make_desc(ab + koff), make_desc(wb1 + koff), idesc, 1u);
         }
-        umma_commit(c.w_empty(ws0));
-        if (PAIR) umma_commit(c.w_empty(ws1));
-        umma_commit(c.a_empty(ast));
+        umma_commit_mc(c.w_empty(ws0), c.mask_w);
+        if (PAIR) umma_commit_mc(c.w_empty(ws1), c.mask_w);
+        umma_commit_mc(c.a_empty(ast), c.mask_a);
         w += PAIR ? 2 : 1;
     }
     umma_commit(c.acc_full(slot0));
@@ -543,8 +564,8 @@ __device__ __forceinline__ void attn_mma(const Ctx2& c, int at, int wt, int na) 
     }
     umma_commit(c.s_full());
     for (int x = 0; x < 2; ++x) {                           // Q and K are free once S is complete
-        umma_commit(c.a_empty((at + x) % kAStages));
-        umma_commit(c.w_empty((wt + x) % kWStg));
+        umma_commit_mc(c.a_empty((at + x) % kAStages), c.mask_a);
+        umma_commit_mc(c.w_empty((wt + x) % kWStg), c.mask_w);
     }
     f2wait(c.p_ready(0), par, 8, c.oi);
     f2wait(c.p_ready(1), par, 8, c.oi);
@@ -571,7 +592,7 @@ __device__ __forceinline__ void attn_mma(const Ctx2& c, int at, int wt, int na) 
     }
     umma_commit(c.o_full(0));
     umma_commit(c.o_full(1));
-    for (int x = 0; x < 2; ++x) umma_commit(c.w_empty((wt + 2 + x) % kWStg));
+    for (int x = 0; x < 2; ++x) umma_commit_mc(c.w_empty((wt + 2 + x) % kWStg), c.mask_w);
 }
 
 __device__ __noinline__ void attn_workers(const Ctx2& c, const F2Fields& op, int na) {
@@ -683,7 +704,8 @@ __device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int
     const int ch = c.r;
     const float* rg = p.ring + ((size_t)id * 2 + ch) * p.T * kD;
     const size_t grow0 = (size_t)c.b * 128 + 64 * ch;
-    const int jnew = p.ds_part ? c.t - 1 : -1;
+    const bool ds = p.ds_part != nullptr && !c.ghost;
+    const int jnew = ds ? c.t - 1 : -1;
     for (int j0 = c.warp; j0 < 64; j0 += 2 * kWorkers2) {          // two rows per pass: both loads in flight
         float v[2][8];
 #pragma unroll
@@ -704,7 +726,7 @@ __device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int
             if (j != jnew) emit_row(p, grow0 + j, c.lane, v[u]);
         }
     }
-    if (p.ds_part && c.warp == kWorkers2 - 1) {
+    if (ds && c.warp == kWorkers2 - 1) {
         // newest embedding: split-K sum of the downsample GEMM, LayerNorm, exact GELU (encoder_components.py:496-511)
         const int n = 2 * c.b + ch;
         const float* pr = p.ds_part + (size_t)n * kD + 8 * c.lane;
@@ -752,12 +774,14 @@ __device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int
             }
         emit_row(p, grow0 + (c.t - 1), c.lane, v8);
     }
-    if (c.r == 0 && c.tid == 0) p.tvalid[c.b] = c.t;
+    if (c.r == 0 && c.tid == 0 && !c.ghost) p.tvalid[c.b] = c.t;
 }
 
 // ============================== op loop ==============================
 __device__ __forceinline__ void op_sync(int cta_only) {
+#ifndef VAPB_F2_NOFENCE
     fence_async_global();
+#endif
     if (cta_only) {
         asm volatile("bar.sync 1, %0;" ::"n"(kThreads2) : "memory");
     } else {
@@ -775,18 +799,23 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
     c.tid = threadIdx.x;
     c.warp = c.tid >> 5;
     c.lane = c.tid & 31;
-    c.r = (int)cluster_ctarank();
-    c.b = blockIdx.x >> 1;
+    const int krank = (int)cluster_ctarank();
+    c.r = krank & 1;
+    c.sidx = krank >> 1;
+    c.b = 2 * (int)(blockIdx.x >> 2) + c.sidx;
+    c.ghost = c.b >= p.B;
+    c.mask_a = (uint16_t)(3u << (2 * c.sidx));
+    c.mask_w = (uint16_t)(5u << c.r);
     c.T = p.T;
     c.oi = 0;
     c.fine = nullptr;
-    const int id = __ldg(p.ids + c.b);
+    const int id = __ldg(p.ids + (c.ghost ? p.B - 1 : c.b));
     const int cnt = __ldg(p.count + id) + 1;           // frames including the one appended this step
     c.t = cnt < p.T ? cnt : p.T;
 
     if (c.warp == kWorkers2 && c.lane == 0) {
-        for (int i = 0; i < kAStages; ++i) { mbar_init(c.a_full(i), 1); mbar_init(c.a_empty(i), 1); }
-        for (int i = 0; i < kWStg; ++i) { mbar_init(c.w_full(i), 1); mbar_init(c.w_empty(i), 1); }
+        for (int i = 0; i < kAStages; ++i) { mbar_init(c.a_full(i), 1); mbar_init(c.a_empty(i), 2); }      // "empty": both consumers of a multicast tile
+        for (int i = 0; i < kWStg; ++i) { mbar_init(c.w_full(i), 1); mbar_init(c.w_empty(i), 2); }
         for (int i = 0; i < kAcc; ++i) { mbar_init(c.acc_full(i), 1); mbar_init(c.acc_empty(i), kWorkers2); }
         mbar_init(c.s_full(), 1);
         for (int i = 0; i < 2; ++i) { mbar_init(c.p_ready(i), 4); mbar_init(c.o_full(i), 1); }
@@ -795,7 +824,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
     if (c.warp == kWorkers2 + 1) tmem_alloc(c.tmem_slot(), 512u);
     if (c.warp == 0) reinterpret_cast<uint32_t*>(c.opslot)[c.lane] = __ldg(reinterpret_cast<const uint32_t*>(&p.ops[0].f) + c.lane);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();          // every CTA's barriers are initialised before any multicast copy or remote commit can reach them
     tc_fence_after();
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c.tmem_base) : "r"(c.tmem_slot()));
 
@@ -865,7 +894,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
                 if (kind == F2_ATTN && elect_one()) attn_tma(c, &p.ops[oi], op, at, wt);
                 __syncwarp();
             } else {
-                const int side = __shfl_sync(0xffffffffu, op.side, 0);
+                const int side = c.ghost ? F2_SIDE_NONE : __shfl_sync(0xffffffffu, op.side, 0);
                 if (side == F2_SIDE_VAD) {
                     // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
                     const float* xr = p.Xf + ((size_t)c.b * 128 + 64 * c.r + (c.t - 1)) * kD + 8 * c.lane;
@@ -901,7 +930,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
         if (dbg) p.dbg[p.n_ops] = clock64();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();          // no CTA leaves while a peer's commits or copies may still target it
     if (c.warp == kWorkers2 + 1) tmem_dealloc(c.tmem_base, 512u);
 }
 
@@ -922,13 +951,13 @@ bool fused2_prepare(std::string& err) {
 
 cudaError_t launch_fused_tf2(const Fused2Params& p, int B, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * B);
+    cfg.gridDim = dim3(4 * ((B + 1) / 2));
     cfg.blockDim = dim3(kThreads2);
     cfg.dynamicSmemBytes = kSmem2;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k_stream_tf2, p);

@@ -53,7 +53,8 @@ struct F2Fields {                    // 128 bytes
     int pad1[4];
 };
 struct alignas(64) F2Op {
-    // GEMM: m[0] / m[1] = A hi / lo planes (box 128 rows x 64), m[2] / m[3] = W hi / lo (box 128 n x 64 k)
+    // GEMM: m[0] / m[1] = A hi / lo planes (box 64 rows x 64: each CTA of a stream multicasts half a tile),
+    //       m[2] / m[3] = W hi / lo (box 64 n x 64 k: each CTA of a column half multicasts half a tile)
     // ATTN: m[0] / m[1] = Q planes (box 128 rows x 64), m[2] / m[3] = K / V planes (box 64 rows x 64)
     CUtensorMap m[4];
     F2Fields f;
@@ -64,6 +65,7 @@ struct Fused2Params {
     const F2Op* ops;
     int n_ops;
     int T;
+    int B;                   // streams in this step (the launch pads an odd batch with a ghost stream on scratch rows)
     const float* ring;       // [max_streams][2][T][256]
     float* ring_w;           // same buffer (the downsample tail appends the newest frame)
     const float* ds_part;    // see fused_tf.cuh

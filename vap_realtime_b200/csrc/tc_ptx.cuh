@@ -166,6 +166,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 8 columns, without the wait: the caller overlaps the load with arithmetic and calls tmem_ld_wait() before using v
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (= 1, unused for swizzled K-major)
 //   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SW128)
@@ -180,6 +189,48 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Exact-erf GELU of a block of values, erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, the level of erff itself).
+// Written stage by stage over groups of 8 so that eight independent dependency chains are in flight: the epilogue
+// warps are few (2 per scheduler) and a GELU is a ~15-instruction chain through two MUFU ops, so without explicit
+// instruction-level parallelism the FFN1 epilogue was latency-bound (measured: 31 k of the 49 k cycles of that op).
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int N>
+__device__ __forceinline__ void gelu_block(float (&v)[N]) {
+    static_assert(N % 8 == 0, "gelu_block works on groups of 8");
+#pragma unroll
+    for (int b = 0; b < N; b += 8) {
+        float z[8], t[8], e[8], pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = fabsf(v[b + i]) * 0.70710678118654752440f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = rcp_fast(fmaf(0.3275911f, z[i], 1.0f));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = ex2_fast(z[i] * z[i] * -1.4426950408889634f);        // exp(-z^2)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = fmaf(1.061405429f, t[i], -1.453152027f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = fmaf(pl[i], t[i], 1.421413741f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = fmaf(pl[i], t[i], -0.284496736f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl[i] = fmaf(pl[i], t[i], 0.254829592f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float er = fmaf(-pl[i] * t[i], e[i], 1.0f);                  // erf(|x| / sqrt 2)
+            v[b + i] = fmaf(0.5f * fabsf(v[b + i]), er, 0.5f * v[b + i]);      // 0.5 x (1 + sign(x) erf(|x| / sqrt 2))
+        }
+    }
+}
 
 // x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi); two elements per packed conversion
 // (cvt.rn.bf16x2.f32 d, a, b puts a in the upper and b in the lower half of d).

@@ -133,7 +133,7 @@ struct vapb_ctx {
                   *Qc2l = nullptr, *H2h = nullptr, *H2l = nullptr;
     F2Op* f2ops = nullptr;
     int n_f2ops = 0;
-    int opt_fused_v = 2;             // 2 = stream kernel v2 where it applies (T <= 64), 1 = always the first-generation kernel
+    int opt_fused_v = 1;             // 1 = first-generation stream kernel (default: measured equal or faster), 2 = second generation where it applies (T <= 64)
     const float* fused_ds_part = nullptr;      // downsample partials handed to the stream kernel (its gather op finishes the embedding)
     long long fused_ds_stride = 0;
     int fused_ds_nsplit = 0;
@@ -618,7 +618,7 @@ int build_fused2(vapb_ctx* c) {
         if (ok && v.W1s) ok = tc_prepare_weight(v.W1s, kFF, kD, v.w1, c->allocs, err);
         if (!ok) return fail(c, VAPB_ECUDA, "stream kernel v2 weights: %s", err.c_str());
     }
-    const size_t R2 = (size_t)c->max_batch * 128;
+    const size_t R2 = ((size_t)c->max_batch + 1) * 128;      // + one scratch slot for the ghost stream of an odd batch
     int rc = 0;
 #define DA2(ptr, n) if (!rc) rc = dalloc(c, &(ptr), (n))
     DA2(c->X2f, R2 * kD);
@@ -650,7 +650,7 @@ int build_fused2(vapb_ctx* c) {
                     __nv_bfloat16* oh, __nv_bfloat16* ol, int ld_out, int cta_sync) {
         F2Op o;
         memset(&o, 0, sizeof o);
-        o.m[0] = A.hi128; o.m[1] = A.lo128; o.m[2] = w.map_hi[1]; o.m[3] = w.map_lo[1];
+        o.m[0] = A.hi64; o.m[1] = A.lo64; o.m[2] = w.map_hi[0]; o.m[3] = w.map_lo[0];
         o.f.kind = F2_GEMM; o.f.K = K; o.f.N = N; o.f.out_mode = out_mode; o.f.n_ln = n_ln; o.f.ln_s = ls; o.f.ln_c = lc; o.f.act = act;
         o.f.out_hi = oh; o.f.out_lo = ol; o.f.ld_out = ld_out; o.f.cta_sync = cta_sync;
         ops.push_back(o);
@@ -709,7 +709,7 @@ void fused_transformer2(Step& s) {
     vapb_ctx* c = s.c;
     Fused2Params p;
     memset(&p, 0, sizeof p);
-    p.ops = c->f2ops; p.n_ops = c->n_f2ops; p.T = c->T;
+    p.ops = c->f2ops; p.n_ops = c->n_f2ops; p.T = c->T; p.B = s.B;
     p.ring = c->ring; p.ring_w = c->ring; p.count = c->count; p.ids = c->ids_dev; p.tvalid = c->tvalid;
     p.ds_part = c->fused_ds_part; p.ds_stride = c->fused_ds_stride; p.ds_nsplit = c->fused_ds_nsplit;
     p.ds_lnw = c->ds_lnw; p.ds_lnb = c->ds_lnb; p.e_out = c->ebuf;
@@ -799,7 +799,9 @@ void enqueue_step(Step& s) {
     // one cluster per stream: a win while all clusters are co-resident (2B <= SM count); bigger batches are served
     // better by the batched per-op kernels, whose GEMM tiles are full (measured B = 128 / 256: r01_n_experiments.md)
     const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
-    const bool use_stream = c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (2 * B <= c->sm_count || c->opt_fused == 2);
+    const bool v2 = c->opt_fused_v == 2 && c->f2ops;
+    const int stream_ctas = v2 ? 4 * ((B + 1) / 2) : 2 * B;       // v2: clusters of four CTAs = two streams
+    const bool use_stream = c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (stream_ctas <= c->sm_count || c->opt_fused == 2);
     // ---- downsample conv over exactly n_lstm frames + LayerNorm + GELU -> ring
     {
         const int Kd = c->n_lstm * kD;
@@ -820,7 +822,7 @@ void enqueue_step(Step& s) {
     if (use_stream) {
         // ---- ring gather, ar_channel, vad, cross layers 0-1 and the K/V of the pruned last layer: ONE launch,
         //      a cluster of two CTAs per stream (fused_tf.cu); then the newest-frame tail of the last layer
-        if (c->opt_fused_v == 2 && c->f2ops) fused_transformer2(s);
+        if (v2) fused_transformer2(s);
         else fused_transformer(s);
         transformer_layer_last(s, c->layers[3], true);
     } else {
