@@ -179,7 +179,7 @@ def test_option_variants_agree(vap_weights, fixture_audio):
     audio, ref = fixture_audio
     outs = {}
     for name, opts in {"default": {}, "lstm_unfused": {"lstm_fused": 0}, "tile64": {"tile_n": 64},
-                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}, "ln_unfused": {"fuse_ln": 0}, "no_k256": {"k256": 0}, "pdl": {"pdl": 1}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "no_fused": {"fused": 0}, "stream_v2": {"fused_v": 2}}.items():
+                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}, "ln_unfused": {"fuse_ln": 0}, "no_k256": {"k256": 0}, "pdl": {"pdl": 1}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "no_fused": {"fused": 0}, "stream_v2": {"fused_v": 2}, "no_tail": {"tail": 0}}.items():
         eng = VapEngine(vap_weights, 20, 50, max_streams=3)
         eng.set_option("gemm", DEF)
         for k, v in opts.items():

@@ -10,7 +10,8 @@ B = int(os.environ.get("B", "64")); T = int(os.environ.get("T", "50"))
 w, _ = bench.load_weights("vap")
 audio = torch.from_numpy(bench.make_audio(B, 8)).cuda()
 configs = {"default": {}, "no_fused": {"fused": 0}, "pdl": {"pdl": 1}, "no_k256": {"k256": 0}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "conv4p_0": {"conv4p": 0}, "conv4p_3": {"conv4p": 3},
-           "ln_unfused": {"fuse_ln": 0}, "lstm_unfused": {"lstm_fused": 0}, "gemm_fp32": {"gemm": 0}}
+           "ln_unfused": {"fuse_ln": 0}, "lstm_unfused": {"lstm_fused": 0}, "gemm_fp32": {"gemm": 0},
+           "no_tail": {"tail": 0}, "stream_v2": {"fused_v": 2}, "lstm_x_tc": {"lstm_x_tc": 1}}
 only = [x for x in os.environ.get("ONLY", "").split(",") if x]
 for name, opts in configs.items():
     if only and name not in only:

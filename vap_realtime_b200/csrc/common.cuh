@@ -201,4 +201,26 @@ struct HeadArgs {
 };
 void launch_head(const HeadArgs& a, cudaStream_t st);
 
+// Newest-frame tail of the pruned last cross layer + Combinator + head in ONE kernel (kernels_simt.cu: k_tail).
+// All weights are k-major transposes ([K][N]) so that a warp reads 128 contiguous bytes of one weight row slice.
+struct TailArgs {
+    const float* Xl;                 // [2B][256] newest frame of every sequence = input rows of the last layer
+    const float* KVs;                // self-attention keys | values of the window: row (n * T + j), 512 floats
+    const float* KVc;                // cross-attention keys | values (projected from the raw sibling rows), same layout
+    const int* tvalid;               // [B]
+    const float *WqT, *WprojT, *WqcT, *WprojcT;      // [256][256]
+    const float *W1T;                // [256][768]
+    const float *W2T;                // [768][256]
+    const float *WaT, *WbT;          // combinator, [256][256]
+    const float *WhT;                // vap head [256][256] (k-major); bc head: [3][256] row-major
+    const float *ln_sa_w, *ln_sa_b, *ln_src_w, *ln_src_b, *ln_ff_w, *ln_ff_b, *comb_lnw, *comb_lnb, *bh;
+    const float *slopes_s, *slopes_c;
+    int n_out, head_kind, B, T;
+    float* out;
+    const IoPtrs* io;
+    int* count;
+    const int* ids;
+};
+void launch_tail(const TailArgs& a, cudaStream_t st);
+
 }  // namespace vapb

@@ -1258,4 +1258,332 @@ __global__ void __launch_bounds__(kHeadWarps * 32) k_head(HeadArgs a) {
 }
 void launch_head(const HeadArgs& a, cudaStream_t st) { launch_k(k_head, dim3(a.B), dim3(kHeadWarps * 32), 0, st, a); }
 
+// -----------------------------------------------------------------------------------------
+// k_tail: everything behind the window-wide K / V projections of the pruned last cross layer, for the newest frame
+// only (modules.py:257-300 restricted to the last position, exact because nothing downstream reads the others:
+// vap_main.py:316-317), then Combinator + head + aggregation (modules.py:461-464, vap_main.py:290-317,
+// objective.py:186-206) and the frame counter.  Replaces nine dependent launches (2 x LN+Q GEMM, 2 x attention,
+// 2 x proj, FFN1, FFN2, head) whose ~10 us each were launch / pipeline-fill latency: the math is 128 rows.
+// One CTA owns kTailStreams streams (2 rows each) end to end in true fp32; activations stay in shared memory, the
+// 3.4 MB of weights stream through once per CTA as k-major float4 rows, 16 loads in flight per thread.
+// -----------------------------------------------------------------------------------------
+constexpr int kTailStreams = 2, kTailRows = 2 * kTailStreams;
+constexpr int kTailCluster = 4;          // CTAs per row group: each computes a quarter of the output columns of every layer
+
+__device__ __forceinline__ uint32_t tail_crank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void tail_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store one float to the same shared-memory location of CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ void tail_dsm_store(float* local, uint32_t rank, float v) {
+    uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
+// out[r][0..255] = sum_k in[r][k] * WT[k][0..255]   (WT row stride ldw), computed by the FOUR CTAs of the cluster: CTA c
+// owns output columns [64c, 64c + 64).  Thread (kq = tid / 16, nq = tid % 16) owns four consecutive outputs over 1/16 of
+// K with all its weight loads in flight at once; the 16 partial sums meet in shared memory, the reduced slice is written
+// into every CTA's `out` through distributed shared memory, one cluster barrier publishes it.  A single SM pulls only
+// ~40 B/clk out of L2: splitting the columns over four SMs is what makes the weight stream short.
+__device__ __forceinline__ void tail_lin256(const float* __restrict__ WT, int ldw, int K, const float* in, int ldin, float* part, float* out,
+                                            int tid, uint32_t crank) {
+    const int nq = tid & 15, kq = tid >> 4;
+    const int kper = K >> 4, k0 = kq * kper;              // 16 (K = 256) or 48 (K = 768)
+    float acc[kTailRows][4];
+#pragma unroll
+    for (int r = 0; r < kTailRows; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+    const float* wp = WT + (size_t)k0 * ldw + 64 * crank + 4 * nq;
+#pragma unroll 4
+    for (int k = 0; k < kper; k += 4) {
+        float4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(k + i) * ldw));
+#pragma unroll
+        for (int r = 0; r < kTailRows; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(in + r * ldin + k0 + k);
+            acc[r][0] = fmaf(x.x, w[0].x, acc[r][0]); acc[r][1] = fmaf(x.x, w[0].y, acc[r][1]); acc[r][2] = fmaf(x.x, w[0].z, acc[r][2]); acc[r][3] = fmaf(x.x, w[0].w, acc[r][3]);
+            acc[r][0] = fmaf(x.y, w[1].x, acc[r][0]); acc[r][1] = fmaf(x.y, w[1].y, acc[r][1]); acc[r][2] = fmaf(x.y, w[1].z, acc[r][2]); acc[r][3] = fmaf(x.y, w[1].w, acc[r][3]);
+            acc[r][0] = fmaf(x.z, w[2].x, acc[r][0]); acc[r][1] = fmaf(x.z, w[2].y, acc[r][1]); acc[r][2] = fmaf(x.z, w[2].z, acc[r][2]); acc[r][3] = fmaf(x.z, w[2].w, acc[r][3]);
+            acc[r][0] = fmaf(x.w, w[3].x, acc[r][0]); acc[r][1] = fmaf(x.w, w[3].y, acc[r][1]); acc[r][2] = fmaf(x.w, w[3].z, acc[r][2]); acc[r][3] = fmaf(x.w, w[3].w, acc[r][3]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kTailRows; ++r)
+        *reinterpret_cast<float4*>(part + ((kq * kTailRows + r) * 64 + 4 * nq)) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    __syncthreads();
+    {   // thread -> (row r = tid / 64, column cidx = tid % 64) of this CTA's slice
+        const int r = tid >> 6, cidx = tid & 63;
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sum += part[(q * kTailRows + r) * 64 + cidx];
+        float* dst = out + r * kD + 64 * crank + cidx;
+#pragma unroll
+        for (uint32_t rk = 0; rk < kTailCluster; ++rk) tail_dsm_store(dst, rk, sum);
+    }
+    tail_cluster_sync();
+}
+
+// LayerNorm(256) of the rows in `x` (shared memory) -> `z`; one warp per row
+__device__ __forceinline__ void tail_ln_rows(const float* x, float* z, const float* w, const float* b, int warp, int lane, bool gelu) {
+    if (warp < kTailRows) {
+        float v[8];
+        load_row8(x + warp * kD, lane, v);
+        warp_norm8(v, 1.0f / 256.0f, w, b, lane);
+        if (gelu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        }
+        store_row8(z + warp * kD, lane, v);
+    }
+    __syncthreads();
+}
+
+// newest-frame attention of one (row, head): every valid key j < t is visible.  Lane = key (see k_attention_last).
+__device__ __forceinline__ void tail_attend(const float* qs, const float* kbase, const float* vbase, int t, float slope, float* os, int lane) {
+    float q[64];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(qs + 4 * i);
+        q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+    }
+    float s[4];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        s[2 * g] = -INFINITY;
+        s[2 * g + 1] = -INFINITY;
+        if (64 * g < t) {
+            const int ja = lane + 64 * g, jb = ja + 32;
+            const float4* ka = reinterpret_cast<const float4*>(kbase + (size_t)min(ja, t - 1) * 512);
+            const float4* kb = reinterpret_cast<const float4*>(kbase + (size_t)min(jb, t - 1) * 512);
+            float4 ra[16], rb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { ra[i] = __ldcg(ka + i); rb[i] = __ldcg(kb + i); }
+            float acca = 0.f, accb = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                acca = fmaf(q[4 * i], ra[i].x, acca); acca = fmaf(q[4 * i + 1], ra[i].y, acca);
+                acca = fmaf(q[4 * i + 2], ra[i].z, acca); acca = fmaf(q[4 * i + 3], ra[i].w, acca);
+                accb = fmaf(q[4 * i], rb[i].x, accb); accb = fmaf(q[4 * i + 1], rb[i].y, accb);
+                accb = fmaf(q[4 * i + 2], rb[i].z, accb); accb = fmaf(q[4 * i + 3], rb[i].w, accb);
+            }
+            if (ja < t) s[2 * g] = acca * 0.0625f + slope * (float)ja;
+            if (jb < t) s[2 * g + 1] = accb * 0.0625f + slope * (float)jb;
+        }
+    }
+    float mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        s[jj] = (lane + 32 * jj < t) ? expf(s[jj] - mx) : 0.f;
+        sum += s[jj];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float o[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        if (64 * g < t) {
+            const int ja = lane + 64 * g, jb = ja + 32;
+            const float4* va = reinterpret_cast<const float4*>(vbase + (size_t)min(ja, t - 1) * 512);
+            const float4* vb = reinterpret_cast<const float4*>(vbase + (size_t)min(jb, t - 1) * 512);
+            float4 ra[16], rb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { ra[i] = __ldcg(va + i); rb[i] = __ldcg(vb + i); }
+            const float pa = s[2 * g] * inv, pb = s[2 * g + 1] * inv;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                o[4 * i] = fmaf(pa, ra[i].x, fmaf(pb, rb[i].x, o[4 * i]));
+                o[4 * i + 1] = fmaf(pa, ra[i].y, fmaf(pb, rb[i].y, o[4 * i + 1]));
+                o[4 * i + 2] = fmaf(pa, ra[i].z, fmaf(pb, rb[i].z, o[4 * i + 2]));
+                o[4 * i + 3] = fmaf(pa, ra[i].w, fmaf(pb, rb[i].w, o[4 * i + 3]));
+            }
+        }
+    }
+    int d0 = 0;
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+        const int bit = 16 >> step, half = 32 >> step;
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? o[i] : o[i + half];
+            const float keep = up ? o[i + half] : o[i];
+            o[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+        if (up) d0 += half;
+    }
+    *reinterpret_cast<float2*>(os + d0) = make_float2(o[0], o[1]);
+}
+
+// the 16 (row, head) attentions of a row group: CTA c of the cluster takes row c (one warp per head), writes the 256
+// outputs to a local scratch row and broadcasts them into every CTA's `ov` row
+__device__ __forceinline__ void tail_attention(const float* KV, int sibling, const float* slopes, const float* qv, float* ov, float* scratch, int b0,
+                                               int B, int T, const int* tvalid, int warp, int lane, uint32_t crank) {
+    const int rr = (int)crank, bs = b0 + (rr >> 1);
+    if (warp < kHeads) {
+        const int h = warp;
+        float* os = scratch + h * 64;
+        if (bs < B) {
+            const int n = 2 * bs + ((rr & 1) ^ sibling);
+            const float* kv = KV + (size_t)n * T * 512 + h * 64;
+            tail_attend(qv + rr * kD + h * 64, kv, kv + kD, tvalid[bs], slopes[h], os, lane);
+        } else {
+            os[lane] = 0.f;
+            os[32 + lane] = 0.f;
+        }
+    }
+    __syncthreads();
+    {
+        const int tid = warp * 32 + lane;
+        const float v = scratch[tid];
+#pragma unroll
+        for (uint32_t rk = 0; rk < kTailCluster; ++rk) tail_dsm_store(ov + rr * kD + tid, rk, v);
+    }
+    tail_cluster_sync();
+}
+
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(256) k_tail(TailArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float tsm[];
+    // local buffers
+    float* x = tsm;                          // [R][256] residual rows
+    float* z = x + kTailRows * kD;           // [R][256] LayerNorm output / scratch
+    float* hd = z + kTailRows * kD;          // [R][768] FFN hidden (GELU applied)
+    float* part = hd + kTailRows * kFF;      // [16][R][64] split-K partial sums of this CTA's column slice
+    // buffers written by every CTA of the cluster (distributed shared memory).  A buffer is written again at the earliest
+    // two cluster barriers after its last readers started, so no CTA can still be reading what a faster peer overwrites.
+    float* bA = part + 16 * kTailRows * 64;  // [R][256] each
+    float* bB = bA + kTailRows * kD;
+    float* bC = bB + kTailRows * kD;
+    float* bD = bC + kTailRows * kD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t crank = tail_crank();
+    const int b0 = (blockIdx.x / kTailCluster) * kTailStreams;
+    const int T = a.T;
+    // rows: rr = 2 * sl + ch  <->  sequence n = 2 * (b0 + sl) + ch; missing streams of the last cluster run on zero rows
+    for (int i = tid; i < kTailRows * kD; i += 256) {
+        const int rr = i >> 8, bs = b0 + (rr >> 1);
+        x[i] = bs < a.B ? a.Xl[(size_t)(2 * bs + (rr & 1)) * kD + (i & 255)] : 0.f;
+    }
+    __syncthreads();
+    tail_cluster_sync();                     // every CTA of the cluster is running before the first remote store
+    // ---- self attention of the newest frame (modules.py:268-272)
+    tail_ln_rows(x, z, a.ln_sa_w, a.ln_sa_b, warp, lane, false);
+    tail_lin256(a.WqT, kD, kD, z, kD, part, bA, tid, crank);
+    tail_attention(a.KVs, 0, a.slopes_s, bA, bB, z, b0, a.B, T, a.tvalid, warp, lane, crank);
+    tail_lin256(a.WprojT, kD, kD, bB, kD, part, bC, tid, crank);
+    for (int i = tid; i < kTailRows * kD; i += 256) x[i] += bC[i];
+    __syncthreads();
+    // ---- cross attention: query from LN_src(x), keys / values of the sibling channel (modules.py:276-283)
+    tail_ln_rows(x, z, a.ln_src_w, a.ln_src_b, warp, lane, false);
+    tail_lin256(a.WqcT, kD, kD, z, kD, part, bA, tid, crank);
+    tail_attention(a.KVc, 1, a.slopes_c, bA, bB, z, b0, a.B, T, a.tvalid, warp, lane, crank);
+    tail_lin256(a.WprojcT, kD, kD, bB, kD, part, bD, tid, crank);
+    for (int i = tid; i < kTailRows * kD; i += 256) x[i] += bD[i];
+    __syncthreads();
+    // ---- feed forward (modules.py:9-21, 285)
+    tail_ln_rows(x, z, a.ln_ff_w, a.ln_ff_b, warp, lane, false);
+    for (int j = 0; j < 3; ++j) {
+        float* o = (j == 1) ? bC : bA;
+        tail_lin256(a.W1T + 256 * j, kFF, kD, z, kD, part, o, tid, crank);
+        for (int i = tid; i < kTailRows * kD; i += 256) hd[(i >> 8) * kFF + 256 * j + (i & 255)] = gelu_erf(o[i]);
+    }
+    __syncthreads();
+    tail_lin256(a.W2T, kD, kFF, hd, kFF, part, bC, tid, crank);
+    for (int i = tid; i < kTailRows * kD; i += 256) x[i] += bC[i];
+    __syncthreads();
+    // ---- Combinator: GELU(LN(h0_a x_ch0)) + GELU(LN(h0_b x_ch1)), one shared LayerNorm (modules.py:461-464)
+    tail_lin256(a.WaT, kD, kD, x, kD, part, bA, tid, crank);          // every row through h0_a: the channel-0 rows are used
+    tail_lin256(a.WbT, kD, kD, x, kD, part, bD, tid, crank);          // every row through h0_b: the channel-1 rows are used
+    for (int i = tid; i < kTailRows * kD; i += 256) {
+        const int rr = i >> 8;
+        z[i] = (rr & 1) ? bD[i] : bA[i];
+    }
+    __syncthreads();
+    tail_ln_rows(z, z, a.comb_lnw, a.comb_lnb, warp, lane, true);
+    for (int i = tid; i < kTailRows * kD; i += 256) {          // comb of stream sl -> row sl of hd (ld 256); the other rows zero
+        const int rr = i >> 8, cidx = i & 255;
+        hd[i] = rr < kTailStreams ? z[(2 * rr) * kD + cidx] + z[(2 * rr + 1) * kD + cidx] : 0.f;
+    }
+    __syncthreads();
+    float* out_base = a.io ? a.io->out : a.out;
+    // ---- head (vap_main.py:290-317 ; vap_bc_main.py:272-277)
+    if (a.head_kind == 0) {
+        tail_lin256(a.WhT, kD, kD, hd, kD, part, bC, tid, crank);     // logits of stream sl in row sl of bC
+        if (crank == 0 && warp < kTailStreams && b0 + warp < a.B) {
+            float lg[8];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                lg[i] = bC[warp * kD + lane + 32 * i] + a.bh[lane + 32 * i];
+                mx = fmaxf(mx, lg[i]);
+            }
+            mx = warp_max(mx);
+            float vals[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cc = lane + 32 * i;
+                const float e = expf(lg[i] - mx);
+                vals[0] += e;
+                vals[1] += e * (float)(((cc >> 0) & 1) + ((cc >> 1) & 1));     // now,    speaker 0: bins 0,1
+                vals[2] += e * (float)(((cc >> 4) & 1) + ((cc >> 5) & 1));     // now,    speaker 1
+                vals[3] += e * (float)(((cc >> 2) & 1) + ((cc >> 3) & 1));     // future, speaker 0: bins 2,3
+                vals[4] += e * (float)(((cc >> 6) & 1) + ((cc >> 7) & 1));     // future, speaker 1
+            }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) vals[k] = warp_sum(vals[k]);
+            if (lane == 0) {
+                float* out = out_base + (size_t)(b0 + warp) * 6;
+                const float inv = 1.0f / vals[0];
+                const float n0 = vals[1] * inv, n1 = vals[2] * inv, f0 = vals[3] * inv, f1 = vals[4] * inv;
+                const float dn = n0 + n1 + kEps, df = f0 + f1 + kEps;         // objective.py:205
+                out[0] = n0 / dn;
+                out[1] = n1 / dn;
+                out[2] = f0 / df;
+                out[3] = f1 / df;            // out[4], out[5] (vad) were written after the ar_channel layer
+                a.count[a.ids[b0 + warp]] += 1;
+            }
+        }
+    } else {
+        if (crank == 0 && warp < kTailStreams && b0 + warp < a.B) {
+            float l3[3];
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sacc = fmaf(hd[warp * kD + lane + 32 * i], a.WhT[o * kD + lane + 32 * i], sacc);
+                l3[o] = warp_sum(sacc) + a.bh[o];
+            }
+            if (lane == 0) {
+                float* out = out_base + (size_t)(b0 + warp) * 6;
+                const float mx = fmaxf(l3[0], fmaxf(l3[1], l3[2]));
+                const float e0 = expf(l3[0] - mx), e1 = expf(l3[1] - mx), e2 = expf(l3[2] - mx);
+                const float inv = 1.0f / (e0 + e1 + e2);
+                out[0] = e1 * inv;          // p_bc_react = softmax[..., 1]   vap_bc_main.py:276
+                out[1] = e2 * inv;          // p_bc_emo   = softmax[..., 2]   vap_bc_main.py:277
+                out[2] = 0.f; out[3] = 0.f; out[4] = 0.f; out[5] = 0.f;
+                a.count[a.ids[b0 + warp]] += 1;
+            }
+        }
+    }
+    tail_cluster_sync();                     // no CTA exits while a peer may still store into its shared memory
+}
+
+constexpr size_t kTailSmem = (size_t)(2 * kTailRows * kD + kTailRows * kFF + 16 * kTailRows * 64 + 4 * kTailRows * kD) * sizeof(float);
+void launch_tail(const TailArgs& a, cudaStream_t st) {
+    static OncePerDevice once;
+    if (once.first()) cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmem);
+    launch_k(k_tail, dim3(kTailCluster * ((a.B + kTailStreams - 1) / kTailStreams)), dim3(256), kTailSmem, st, a);
+}
+
 }  // namespace vapb

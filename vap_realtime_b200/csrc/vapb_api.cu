@@ -86,12 +86,18 @@ struct vapb_ctx {
     float *w0 = nullptr, *b0 = nullptr, *cn0w = nullptr, *cn0b = nullptr;
     ConvLayer conv[4];
     float *Wih = nullptr, *Whh = nullptr, *b_lstm = nullptr;
+    TcWeight tc_ih;                  // W_ih planes: the LSTM input projection on tcgen05 (option lstm_x_tc); the recurrence stays fp32
+    int opt_lstm_x_tc = 0;
     float *Wds = nullptr, *bds = nullptr, *ds_lnw = nullptr, *ds_lnb = nullptr;
     TcWeight tc_ds;
     LayerWeights layers[4];          // [0] = ar_channel.layers.0, [1..3] = ar.layers.0..2
     float *Wa = nullptr, *Wb = nullptr, *comb_lnw = nullptr, *comb_lnb = nullptr;
     float *Wh = nullptr, *bh = nullptr;
     int n_out = 256;
+    // k-major transposes for the fused newest-frame tail (k_tail): last cross layer + combinator + head
+    float *t_WqT = nullptr, *t_WprojT = nullptr, *t_WqcT = nullptr, *t_WprojcT = nullptr, *t_W1T = nullptr, *t_W2T = nullptr,
+          *t_WaT = nullptr, *t_WbT = nullptr, *t_WhT = nullptr;
+    int opt_tail = 1;                // 1 = k_tail (one kernel), 0 = the nine per-op kernels
     float *va_w = nullptr, *va_b = nullptr;
 
     // per-stream state
@@ -265,6 +271,15 @@ struct Loader {
         const HostTensor* h = get(name, shape);
         if (!h) return nullptr;
         return upload(std::vector<float>(h->data, h->data + h->numel));
+    }
+    // [N][K] row-major -> [K][N] (k-major), for kernels that read a weight row slice per warp
+    float* upT(const std::string& name, uint32_t N, uint32_t K) {
+        const HostTensor* h = get(name, {N, K});
+        if (!h) return nullptr;
+        std::vector<float> v((size_t)N * K);
+        for (uint32_t n = 0; n < N; ++n)
+            for (uint32_t k = 0; k < K; ++k) v[(size_t)k * N + n] = h->data[(size_t)n * K + k];
+        return upload(v);
     }
     // Conv1d weight [Cout][Cin][k] -> GEMM weight [Cout][k*Cin] (K index = tap*Cin + cin), matching
     // the channels-last activation rows (tap-major K).
@@ -440,7 +455,7 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
 
 // Final cross layer with the query side restricted to the newest frame of every sequence (exact:
 // nothing downstream reads the other positions, vap_main.py:316-317).  K/V still cover the window.
-void transformer_layer_last(Step& s, const LayerWeights& lw, bool kv_done = false) {
+void transformer_layer_last(Step& s, const LayerWeights& lw, bool kv_done = false, bool query_side = true) {
     vapb_ctx* c = s.c;
     const int NL = 2 * s.B, R = NL * c->T;
     const RowMap pd = plain_map(kD), pf = plain_map(kFF), p2 = plain_map(2 * kD);
@@ -467,6 +482,7 @@ void transformer_layer_last(Step& s, const LayerWeights& lw, bool kv_done = fals
         ln_gemm("gemm_ln_kv_self", c->X, c->Z, R, lw.ln_sa_w, lw.ln_sa_b, lw.sa.Wqkv + (size_t)kD * kD, &lw.sa.tc_kv, c->QKV, p2, 2 * kD, 0);
         launch_gather_last(c->X, c->tvalid, c->Xl, NL, c->T, s.st); mark(s, "gather_last");
     }
+    if (!query_side) return;          // the fused tail kernel (k_tail) does the rest
     // self attention of the newest frame
     ln_gemm("gemm_ln_q_last", c->Xl, c->Zl, NL, lw.ln_sa_w, lw.ln_sa_b, lw.sa.Wqkv, &lw.sa.tc_q, c->Ql, pd, kD, 0);
     attn_last(c->Ql, c->QKV, c->QKV + kD, 2 * kD, lw.sa.slopes, 0);
@@ -779,7 +795,7 @@ void enqueue_step(Step& s) {
         am.offset = (long long)(c->halo[4] + 1) * kD;
         const RowMap g4 = plain_map(4 * kD);
         // input projection for all n_lstm frames at once (fp32), then the fused recurrence
-        gemm(s, "gemm_lstm_x", c->act[4], am, c->Wih, nullptr, c->b_lstm, nullptr, g4, c->Gx, g4, NC * c->n_lstm, 4 * kD, kD, 0);
+        gemm(s, "gemm_lstm_x", c->act[4], am, c->Wih, c->opt_lstm_x_tc ? &c->tc_ih : nullptr, c->b_lstm, nullptr, g4, c->Gx, g4, NC * c->n_lstm, 4 * kD, kD, 0);
         if (c->opt_lstm_fused) {
             launch_lstm_recurrent(c->Gx, c->Whh, c->hS, c->cS, c->ids_dev, c->Y, NC, c->n_lstm, st); mark(s, "lstm_recurrent");
         } else {
@@ -824,7 +840,7 @@ void enqueue_step(Step& s) {
         //      a cluster of two CTAs per stream (fused_tf.cu); then the newest-frame tail of the last layer
         if (v2) fused_transformer2(s);
         else fused_transformer(s);
-        transformer_layer_last(s, c->layers[3], true);
+        transformer_layer_last(s, c->layers[3], true, !c->opt_tail);
     } else {
     // ---- window of the last T embeddings, oldest first (vap_main.py:274-283)
     launch_gather_ring(c->ring, c->count, c->ids_dev, c->X, c->tvalid, B, T, st); mark(s, "gather_ring");
@@ -838,10 +854,24 @@ void enqueue_step(Step& s) {
     }
     // ---- ar: three TransformerStereoLayers (modules.py:289-300, 395-423)
     for (int li = 0; li < 3; ++li) {
-        if (li == 2 && prune) transformer_layer_last(s, c->layers[3]);
+        if (li == 2 && prune) transformer_layer_last(s, c->layers[3], false, !c->opt_tail);
         else transformer_layer(s, c->layers[1 + li]);
         tap_copy(s, c->tap_cross[li], c->X, RX);
     }
+    }
+    if (prune && c->opt_tail) {
+        // ---- newest-frame side of the pruned layer + combinator + head + aggregation + frame counters: one kernel
+        const LayerWeights& lw = c->layers[3];
+        TailArgs t;
+        t.Xl = c->Xl; t.KVs = c->QKV; t.KVc = c->KVc; t.tvalid = c->tvalid;
+        t.WqT = c->t_WqT; t.WprojT = c->t_WprojT; t.WqcT = c->t_WqcT; t.WprojcT = c->t_WprojcT; t.W1T = c->t_W1T; t.W2T = c->t_W2T;
+        t.WaT = c->t_WaT; t.WbT = c->t_WbT; t.WhT = c->t_WhT;
+        t.ln_sa_w = lw.ln_sa_w; t.ln_sa_b = lw.ln_sa_b; t.ln_src_w = lw.ln_src_w; t.ln_src_b = lw.ln_src_b; t.ln_ff_w = lw.ln_ff_w; t.ln_ff_b = lw.ln_ff_b;
+        t.comb_lnw = c->comb_lnw; t.comb_lnb = c->comb_lnb; t.bh = c->bh; t.slopes_s = lw.sa.slopes; t.slopes_c = lw.slopes_c;
+        t.n_out = c->n_out; t.head_kind = c->head_kind; t.B = B; t.T = T;
+        t.out = s.out; t.io = s.io; t.count = c->count; t.ids = c->ids_dev;
+        launch_tail(t, st); mark(s, "tail");
+        return;
     }
     // ---- combinator + projection head + aggregation; advances the frame counters
     HeadArgs h;
@@ -977,6 +1007,18 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         c->Wh = ld.up("bc_head.weight", {3, 256});
         c->bh = ld.up("bc_head.bias", {3});
     }
+    {
+        const std::string p3 = "ar.layers.2.";
+        c->t_WqT = ld.upT(p3 + "mha.query.weight", 256, 256);
+        c->t_WprojT = ld.upT(p3 + "mha.proj.weight", 256, 256);
+        c->t_WqcT = ld.upT(p3 + "mha_cross.query.weight", 256, 256);
+        c->t_WprojcT = ld.upT(p3 + "mha_cross.proj.weight", 256, 256);
+        c->t_W1T = ld.upT(p3 + "ffnetwork.0.weight", 768, 256);
+        c->t_W2T = ld.upT(p3 + "ffnetwork.3.weight", 256, 768);
+        c->t_WaT = ld.upT("ar.combinator.h0_a.weight", 256, 256);
+        c->t_WbT = ld.upT("ar.combinator.h0_b.weight", 256, 256);
+        c->t_WhT = head_kind == VAPB_HEAD_VAP ? ld.upT("vap_head.weight", 256, 256) : c->Wh;      // bc head: [3][256] as is
+    }
     build_v2_weights(ld, c);
     if (!ld.ok) FAIL_CREATE(VAPB_EWEIGHTS, "%s", ld.err.c_str());
 
@@ -1041,6 +1083,7 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         bool ok = true;
         for (int i = 0; i < 4 && ok; ++i) ok = tc_prepare_weight(c->conv[i].W, kD, c->conv[i].k * kD, c->conv[i].tc, c->allocs, terr);
         if (ok) ok = tc_prepare_weight(c->Wds, kD, c->n_lstm * kD, c->tc_ds, c->allocs, terr);
+        if (ok) ok = tc_prepare_weight(c->Wih, 4 * kD, kD, c->tc_ih, c->allocs, terr);
         for (int l = 0; l < 4 && ok; ++l) {
             LayerWeights& lw = c->layers[l];
             ok = tc_prepare_weight(lw.sa.Wqkv, 3 * kD, kD, lw.sa.tc_qkv, c->allocs, terr) &&
@@ -1264,7 +1307,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v" || k == "tail" || k == "lstm_x_tc") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -1283,6 +1326,8 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "fused") h->opt_fused = value;      // 0 off, 1 auto (one wave of clusters), 2 always
         else if (k == "fused_dbg") h->opt_fused_dbg = value;
         else if (k == "fused_v") h->opt_fused_v = value == 1 ? 1 : 2;
+        else if (k == "tail") h->opt_tail = value ? 1 : 0;
+        else if (k == "lstm_x_tc") h->opt_lstm_x_tc = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -1319,6 +1364,8 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "cluster2") *value = h->tcws.cluster2;
     else if (k == "fused") *value = h->opt_fused;
     else if (k == "fused_dbg") *value = h->opt_fused_dbg;
+    else if (k == "tail") *value = h->opt_tail;
+    else if (k == "lstm_x_tc") *value = h->opt_lstm_x_tc;
     else if (k == "fused_v") *value = (h->opt_fused_v == 2 && h->f2ops) ? 2 : 1;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
