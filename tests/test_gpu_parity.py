@@ -310,3 +310,66 @@ def test_stream_kernel_window_edges(T, gen):
     assert fused.last_launch_count < plain.last_launch_count
     assert worst_or < 1e-4
     assert worst_ab < 5e-5
+
+
+def test_layer0_qkv_cache_is_exact():
+    """Layer-0 Q / K / V cache of the batched path (LN(e_j) Wq/Wk/Wv of ar_channel depends on the frame
+    only, ALiBi is shift invariant): results must be BIT-identical to recomputing the projections of the whole window
+    every step -- through warm-up, the sliding window (T = 12, 40 steps), a late join, a reset and a state import."""
+    w = weights.random_tensors(seed=17)
+    T, n_steps = 12, 40
+    engs = []
+    for cache in (1, 0):
+        e = VapEngine(w, 20, T, max_streams=8, max_batch=4)
+        e.set_option("gemm", 1)
+        e.set_option("fused", 0)             # batched per-op kernels (what batches above ~74 streams run)
+        e.set_option("qkv_cache", cache)
+        engs.append(e)
+    oracle = VapOracle(w, 20, T, "vap")
+    slots = [5, 1, 6]
+    join = [0, 0, 7]
+    audio = [synthetic_audio(40 + s, n_steps) for s in range(3)]
+    states = [OracleState(1) for _ in slots]
+    local = [0] * 3
+    worst = 0.0
+    for step in range(n_steps):
+        if step == 21:                       # stream 1 hangs up, a new dialogue takes its slot
+            for e in engs:
+                e.reset([slots[1]])
+            states[1] = OracleState(1)
+            local[1] = 0
+        if step == 30:                       # stream 0 migrates to another slot: the cache of the new slot is rebuilt from the ring
+            for e in engs:
+                e.import_state(3, e.export_state(slots[0]))
+            slots[0] = 3
+        active = [k for k in range(3) if step >= join[k]]
+        a = np.stack([chunk(audio[k], local[k]) for k in active])
+        ids = [slots[k] for k in active]
+        x = engs[0].step(torch.from_numpy(a).cuda(), ids).cpu().numpy()
+        y = engs[1].step(torch.from_numpy(a).cuda(), ids).cpu().numpy()
+        assert np.array_equal(x, y), (step, np.abs(x - y).max())
+        for row, k in enumerate(active):
+            want = oracle.step(a[row:row + 1], states[k]).numpy()[0]
+            worst = max(worst, float(np.abs(x[row] - want).max()))
+            local[k] += 1
+    print(f"layer-0 Q/K/V cache: bit-identical to the recompute path over {n_steps} steps ({engs[0].last_launch_count} vs "
+          f"{engs[1].last_launch_count} kernels/step), vs oracle {worst:.2e}")
+    assert worst < 1e-4
+    assert engs[0].last_launch_count > engs[1].last_launch_count - 5
+
+
+def test_layer0_qkv_cache_survives_path_switches(vap_weights, fixture_audio):
+    """A server's batch size wanders: the same streams are stepped by the per-stream cluster kernel (small batches, layer 0
+    recomputed) and by the batched kernels (large batches, layer 0 cached).  Stale cache rows must be rebuilt."""
+    audio, ref = fixture_audio
+    eng = VapEngine(vap_weights, 20, 50, max_streams=2)
+    eng.set_option("gemm", 1)
+    worst = 0.0
+    for n in range(70):
+        if n % 7 == 0:
+            eng.set_option("fused", 0 if (n // 7) % 2 else 2)
+        a = torch.from_numpy(np.ascontiguousarray(chunk(audio, n)))[None].cuda()
+        got = eng.step(a, [1]).cpu().numpy()[0]
+        worst = max(worst, float(np.abs(got - ref[n]).max()))
+    print(f"path switches every 7 steps: max|d| vs reference fixture = {worst:.2e}")
+    assert worst < 1e-4

@@ -179,8 +179,14 @@ struct AttnArgs {
     int n_seq;                     // 2B sequences of T rows each
     int T;
     int sibling;                   // 1: K/V rows come from the other channel of the same stream
+    // Layer-0 Q/K/V cache: when ring_ids != null, Q / K / V point at the per-stream ring [max_streams][2][T][ld] and the row of
+    // logical position j of sequence n is ring slot (count + 1 - t + j) % T of stream ring_ids[n / 2] (O stays in batch order)
+    const int* ring_ids = nullptr;
+    const int* ring_count = nullptr;
 };
 void launch_attention(const AttnArgs& a, cudaStream_t st);
+// rows [n][768] of freshly projected Q|K|V of the newest frame -> ring slot count % T of their streams
+void launch_qkv_append(const float* qkv_new, float* qkv_ring, const int* count, const int* ids, int B, int T, cudaStream_t st);
 // last-row-only variants used when the final cross layer is pruned to the newest frame
 void launch_gather_last(const float* X, const int* tvalid, float* Xl, int n_seq, int T, cudaStream_t st);
 void launch_attention_last(const AttnArgs& a, cudaStream_t st);   // Q, O: [n_seq][256] compact; K, V: full rows

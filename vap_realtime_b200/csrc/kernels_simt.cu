@@ -738,9 +738,20 @@ __global__ void __launch_bounds__(kAttnWarps * 32) k_attention(AttnArgs a) {
     const int t = a.tvalid[n >> 1];
     const int kvn = a.sibling ? (n ^ 1) : n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // layer-0 Q/K/V cache: rows live in the stream's ring, oldest frame at slot (frames - t) % T
+    long long ring_base = -1;
+    int ring_first = 0;
+    if (a.ring_ids) {
+        const int id = a.ring_ids[n >> 1];
+        ring_base = ((long long)id * 2 + (n & 1)) * T;
+        ring_first = (a.ring_count[id] + 1 - t) % T;
+    }
+    auto in_row = [&](int seq, int pos) -> size_t {
+        return ring_base >= 0 ? (size_t)(ring_base + (ring_first + pos) % T) : (size_t)seq * T + pos;
+    };
     for (int i = threadIdx.x; i < t * 16; i += blockDim.x) {
         const int j = i >> 4, q = (i & 15) * 4;
-        const size_t r = (size_t)kvn * T + j;
+        const size_t r = in_row(kvn, j);
         const float4 kk = *reinterpret_cast<const float4*>(a.K + r * a.ldk + h * 64 + q);
         const float4 vv = *reinterpret_cast<const float4*>(a.V + r * a.ldv + h * 64 + q);
         float* dk = sK + j * 65 + q;
@@ -758,7 +769,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) k_attention(AttnArgs a) {
             orow[lane + 32] = 0.f;
             continue;
         }
-        const float* qrow = a.Q + ((size_t)n * T + i) * a.ldq + h * 64;
+        const float* qrow = a.Q + in_row(n, i) * a.ldq + h * 64;
         q[lane] = qrow[lane];
         q[lane + 32] = qrow[lane + 32];
         __syncwarp();
@@ -932,8 +943,23 @@ __global__ void __launch_bounds__(128) k_attention_rk(AttnArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(256) k_qkv_append(const float* __restrict__ qkv_new, float* __restrict__ qkv_ring, const int* __restrict__ count,
+                                                    const int* __restrict__ ids, int B, int T) {
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.x;                  // sequence 2b + ch
+    const int id = ids[n >> 1];
+    const int slot = count[id] % T;            // the counter is advanced at the end of the step
+    const float4* src = reinterpret_cast<const float4*>(qkv_new + (size_t)n * 3 * kD);
+    float4* dst = reinterpret_cast<float4*>(qkv_ring + (((size_t)id * 2 + (n & 1)) * T + slot) * 3 * kD);
+    if (threadIdx.x < 3 * kD / 4) dst[threadIdx.x] = src[threadIdx.x];
+}
+void launch_qkv_append(const float* qkv_new, float* qkv_ring, const int* count, const int* ids, int B, int T, cudaStream_t st) {
+    launch_k(k_qkv_append, dim3(2 * B), dim3(256), 0, st, qkv_new, qkv_ring, count, ids, B, T);
+}
+
 void launch_attention(const AttnArgs& a, cudaStream_t st) {
-    if (a.T <= 64 && g_attn_rk) {
+    if (a.T <= 64 && g_attn_rk && !a.ring_ids) {
         const size_t sm = (size_t)(a.T * 64 + 4 * 256 + 4 * 256) * sizeof(float);
         dim3 grid(a.n_seq, kHeads);
         if (a.T <= 32) launch_k(k_attention_rk<1>, grid, dim3(128), sm, st, a);

@@ -104,6 +104,13 @@ struct vapb_ctx {
     float *hS = nullptr, *cS = nullptr, *ring = nullptr;
     int* count = nullptr;
 
+    // layer-0 Q/K/V cache (batched path): LN(e_j) Wq / Wk / Wv of ar_channel depends on frame j only (no positional input,
+    // ALiBi is a shift-invariant key bias: modules.py:93-95, 170-212), so it is projected once when the frame arrives and
+    // kept in a per-stream ring next to the embedding ring; host-side frame counters know which streams are up to date
+    float* qkv_ring = nullptr;       // [max_streams][2][T][768]
+    float* QKVn = nullptr;           // [2 max_batch][768] projections of the newest frame
+    std::vector<long long> h_cnt, h_qkv;      // frames seen per stream / frames covered by its cached rows (-1 = stale)
+    int opt_qkv_cache = 1;
     // per-step workspaces (sized for max_batch)
     uint8_t* iobuf_dev = nullptr;    // [IoPtrs (16 B)][ids: max_batch x int32], refreshed by ONE H2D copy per step
     uint8_t* iobuf_pinned = nullptr;
@@ -392,15 +399,18 @@ void tap_copy(Step& s, float* dst, const float* src, size_t n) {
 }
 
 void attention(Step& s, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O,
-               const float* slopes, int sibling) {
+               const float* slopes, int sibling, bool ring = false) {
     AttnArgs a;
     a.Q = Q; a.ldq = ldq; a.K = K; a.ldk = ldk; a.V = V; a.ldv = ldv; a.O = O; a.ldo = kD;
     a.tvalid = s.c->tvalid; a.slopes = slopes; a.n_seq = 2 * s.B; a.T = s.c->T; a.sibling = sibling;
+    if (ring) { a.ring_ids = s.c->ids_dev; a.ring_count = s.c->count; }
     launch_attention(a, s.st);
     mark(s, sibling ? "attn_cross" : "attn_self");
 }
 
-void transformer_layer(Step& s, const LayerWeights& lw) {
+bool qkv_cache_active(const vapb_ctx* c) { return c->opt_qkv_cache && c->opt_gemm == 1 && c->opt_fuse_ln && !c->opt_keep_taps && c->qkv_ring; }
+
+void transformer_layer(Step& s, const LayerWeights& lw, bool qkv_cached = false) {
     vapb_ctx* c = s.c;
     const int R = 2 * s.B * c->T;
     const RowMap pd = plain_map(kD), pf = plain_map(kFF), p3 = plain_map(3 * kD), p2 = plain_map(2 * kD);
@@ -424,6 +434,12 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
     // self attention block (modules.py:268-272)
     // LayerNorm is a prologue of the consuming GEMM on the tensor-core path, a kernel of its own otherwise
     const bool fuse_ln = c->opt_gemm == 1 && c->opt_fuse_ln;
+    if (qkv_cached) {
+        // Q / K / V of every window frame are already in the stream's ring: only the newest frame is projected (2B rows)
+        gemm(s, "gemm_ln_qkv_new", c->ebuf, pd, lw.sa.Wqkv, &lw.sa.tc_qkv, nullptr, nullptr, pd, c->QKVn, p3, 2 * s.B, 3 * kD, kD, 0, lw.ln_sa_w, lw.ln_sa_b);
+        launch_qkv_append(c->QKVn, c->qkv_ring, c->count, c->ids_dev, s.B, c->T, s.st); mark(s, "qkv_append");
+        attention(s, c->qkv_ring, 3 * kD, c->qkv_ring + kD, 3 * kD, c->qkv_ring + 2 * kD, 3 * kD, c->O, lw.sa.slopes, 0, true);
+    } else {
     if (fuse_ln) {
         gemm(s, "gemm_ln_qkv", c->X, pd, lw.sa.Wqkv, &lw.sa.tc_qkv, nullptr, nullptr, pd, c->QKV, p3, R, 3 * kD, kD, 0, lw.ln_sa_w, lw.ln_sa_b);
     } else {
@@ -431,6 +447,7 @@ void transformer_layer(Step& s, const LayerWeights& lw) {
         gemm(s, "gemm_qkv", c->Z, pd, lw.sa.Wqkv, &lw.sa.tc_qkv, nullptr, nullptr, pd, c->QKV, p3, R, 3 * kD, kD, 0);
     }
     attention(s, c->QKV, 3 * kD, c->QKV + kD, 3 * kD, c->QKV + 2 * kD, 3 * kD, c->O, lw.sa.slopes, 0);
+    }
     if (fork) cudaStreamWaitEvent(s.st, c->ev_join, 0);      // X is overwritten next: the side branch must have read it
     gemm(s, "gemm_proj", c->O, pd, lw.sa.Wproj, &lw.sa.tc_proj, nullptr, c->X, pd, c->X, pd, R, kD, kD, 0);
     if (lw.cross) {
@@ -847,7 +864,7 @@ void enqueue_step(Step& s) {
     const size_t RX = (size_t)NC * T * kD;
     tap_copy(s, c->tap_xin, c->X, RX);
     // ---- ar_channel: one TransformerLayer per channel, shared weights (vap_main.py:285-286)
-    transformer_layer(s, c->layers[0]);
+    transformer_layer(s, c->layers[0], qkv_cache_active(c));
     tap_copy(s, c->tap_chan, c->X, RX);
     if (c->head_kind == VAPB_HEAD_VAP) {
         launch_vad(c->X, c->tvalid, c->va_w, c->va_b, s.out, s.io, B, T, st); mark(s, "vad");
@@ -881,6 +898,45 @@ void enqueue_step(Step& s) {
     h.logits_tap = c->opt_keep_taps ? c->tap_logits : nullptr;
     h.count = c->count; h.ids = c->ids_dev; h.B = B; h.T = T; h.head_kind = c->head_kind;
     launch_head(h, st); mark(s, "head");
+}
+
+// same decision as enqueue_step: does a batch of B run the per-stream cluster kernel (which recomputes layer 0)?
+bool step_uses_stream(const vapb_ctx* c, int B) {
+    const bool prune = c->opt_prune && !c->opt_keep_taps;
+    const bool v2 = c->opt_fused_v == 2 && c->f2ops;
+    const int stream_ctas = v2 ? 4 * ((B + 1) / 2) : 2 * B;
+    return c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (stream_ctas <= c->sm_count || c->opt_fused == 2);
+}
+
+// Layer-0 Q/K/V cache bookkeeping in front of a step: a stream whose cached rows do not cover all its frames (it was
+// stepped by the cluster kernel, imported, or the cache was off) gets its whole window re-projected from the embedding
+// ring: one LN + GEMM over its 2T ring rows, outside the step graph.  Steady state: nothing to do.
+int qkv_cache_pre_step(vapb_ctx* c, const int* ids, int B, cudaStream_t st) {
+    if (!qkv_cache_active(c) || step_uses_stream(c, B)) return 0;
+    const LayerWeights& lw = c->layers[0];
+    for (int i = 0; i < B; ++i) {
+        const int id = ids[i];
+        if (c->h_cnt[id] == 0 || c->h_qkv[id] == c->h_cnt[id]) continue;
+        GemmArgs g;
+        g.A = c->ring + (size_t)id * 2 * c->T * kD; g.amap = plain_map(kD);
+        g.W = lw.sa.Wqkv; g.bias = nullptr; g.R = nullptr; g.rmap = plain_map(kD);
+        g.C = c->qkv_ring + (size_t)id * 2 * c->T * 3 * kD; g.cmap = plain_map(3 * kD);
+        g.M = 2 * c->T; g.N = 3 * kD; g.K = kD; g.act = 0; g.ln_w = lw.ln_sa_w; g.ln_b = lw.ln_sa_b;
+        launch_gemm_tc(g, lw.sa.tc_qkv, c->tcws, st);
+        c->h_qkv[id] = c->h_cnt[id];
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, VAPB_ECUDA, "Q/K/V cache rebuild failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+void qkv_cache_post_step(vapb_ctx* c, const int* ids, int B) {
+    const bool cached = qkv_cache_active(c) && !step_uses_stream(c, B);
+    for (int i = 0; i < B; ++i) {
+        const int id = ids[i];
+        const bool was_current = c->h_qkv[id] == c->h_cnt[id];
+        c->h_cnt[id] += 1;
+        if (cached && was_current) c->h_qkv[id] = c->h_cnt[id];
+    }
 }
 
 int check_ids(vapb_ctx* c, const int* ids, int B) {
@@ -1054,6 +1110,8 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     DA(c->Ql, NC * kD);
     DA(c->Ol, NC * kD);
     DA(c->Hl, NC * kFF);
+    DA(c->qkv_ring, MS * 2 * c->T * 3 * kD);
+    DA(c->QKVn, NC * 3 * kD);
     DA(c->audio_stage, MB * 2 * c->S);
     DA(c->out_stage, MB * 6);
 #undef DA
@@ -1103,6 +1161,8 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         if (!ok) FAIL_CREATE(VAPB_ECUDA, "tcgen05 setup failed: %s", terr.c_str());
     }
 
+    c->h_cnt.assign(MS, 0);
+    c->h_qkv.assign(MS, 0);
     if (build_fused_ops(c) != 0) FAIL_CREATE(VAPB_ECUDA, "%s", c->err.c_str());
     if (build_fused2(c) != 0) FAIL_CREATE(VAPB_ECUDA, "%s", c->err.c_str());
 
@@ -1145,6 +1205,8 @@ int vapb_reset_streams(vapb_handle h, const int* ids, int n) {
         CK(h, cudaMemset(h->ring, 0, rg * h->max_streams));
         CK(h, cudaMemset(h->count, 0, sizeof(int) * h->max_streams));
         CK(h, cudaDeviceSynchronize());      // the memsets ran on the legacy stream: later steps may use any stream
+        std::fill(h->h_cnt.begin(), h->h_cnt.end(), 0);
+        std::fill(h->h_qkv.begin(), h->h_qkv.end(), 0);
         return VAPB_OK;
     }
     for (int i = 0; i < n; ++i) {
@@ -1154,6 +1216,8 @@ int vapb_reset_streams(vapb_handle h, const int* ids, int n) {
         CK(h, cudaMemset(h->cS + (size_t)id * 2 * kD, 0, st));
         CK(h, cudaMemset(h->ring + (size_t)id * 2 * h->T * kD, 0, rg));
         CK(h, cudaMemset(h->count + id, 0, sizeof(int)));
+        h->h_cnt[id] = 0;
+        h->h_qkv[id] = 0;
     }
     CK(h, cudaDeviceSynchronize());
     return VAPB_OK;
@@ -1174,6 +1238,8 @@ int vapb_step(vapb_handle h, const float* audio, const int* ids, int B, float* o
         CK(h, cudaEventRecord(h->ev_in, caller));
         CK(h, cudaStreamWaitEvent(st, h->ev_in, 0));
     }
+    rc = qkv_cache_pre_step(h, ids, B, st);
+    if (rc) return rc;
     // {audio, out} + ids -> device in ONE copy.  The pinned staging buffer is reused, so wait for the previous copy first.
     if (h->last_B != 0) CK(h, cudaEventSynchronize(h->ev0));
     {
@@ -1220,6 +1286,7 @@ int vapb_step(vapb_handle h, const float* audio, const int* ids, int B, float* o
         h->launches = s.n;
         CK(h, cudaGetLastError());
     }
+    qkv_cache_post_step(h, ids, B);
     if (h->opt_timing) {
         CK(h, cudaEventRecord(h->ev1, st));
         h->timed = true;
@@ -1290,6 +1357,8 @@ int vapb_import_state(vapb_handle h, int id, const float* state) {
             memcpy(raw.data() + ((size_t)ch * T + slot) * kD, r + ((size_t)ch * T + j) * kD, kD * sizeof(float));
         }
     CK(h, cudaMemcpy(h->ring + (size_t)id * 2 * T * kD, raw.data(), raw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->h_cnt[id] = cnt;
+    h->h_qkv[id] = -1;           // cached layer-0 projections no longer match the ring: rebuilt before the next batched step
     return VAPB_OK;
 }
 
@@ -1307,7 +1376,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v" || k == "tail" || k == "lstm_x_tc") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v" || k == "tail" || k == "lstm_x_tc" || k == "qkv_cache") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -1328,6 +1397,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "fused_v") h->opt_fused_v = value == 1 ? 1 : 2;
         else if (k == "tail") h->opt_tail = value ? 1 : 0;
         else if (k == "lstm_x_tc") h->opt_lstm_x_tc = value ? 1 : 0;
+        else if (k == "qkv_cache") h->opt_qkv_cache = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -1366,6 +1436,7 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "fused_dbg") *value = h->opt_fused_dbg;
     else if (k == "tail") *value = h->opt_tail;
     else if (k == "lstm_x_tc") *value = h->opt_lstm_x_tc;
+    else if (k == "qkv_cache") *value = h->opt_qkv_cache;
     else if (k == "fused_v") *value = (h->opt_fused_v == 2 && h->f2ops) ? 2 : 1;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
@@ -1440,6 +1511,8 @@ int vapb_profile_step(vapb_handle h, const float* audio, const int* ids, int B, 
     CK(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     CK(h, cudaStreamSynchronize(st));
+    rc = qkv_cache_pre_step(h, ids, B, st);
+    if (rc) return rc;
     memcpy(h->iobuf_pinned + sizeof(IoPtrs), ids, sizeof(int) * B);
     CK(h, cudaMemcpyAsync(h->ids_dev, h->iobuf_pinned + sizeof(IoPtrs), sizeof(int) * B, cudaMemcpyHostToDevice, st));
     h->last_B = B;
@@ -1452,6 +1525,7 @@ int vapb_profile_step(vapb_handle h, const float* audio, const int* ids, int B, 
     CK(h, cudaEventRecord(h->ev0, st));
     enqueue_step(s);
     h->launches = s.n;
+    qkv_cache_post_step(h, ids, B);
     cudaError_t e = cudaStreamSynchronize(st);
     std::vector<std::pair<std::string, std::pair<float, int>>> agg;
     cudaEvent_t prev = e0;
