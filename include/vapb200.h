@@ -105,6 +105,20 @@ VAPB_API int vapb_step(vapb_handle h, const float* audio, const int* stream_ids,
 VAPB_API int vapb_step_host(vapb_handle h, const float* audio, const int* stream_ids, int B, float* out,
                    void* cuda_stream);
 
+/*
+ * Bulk offline scoring of one two-channel recording: the result of replaying it frame by frame through
+ * process_vap the way rvap/vap_main/vap_offline.py:51-73 does (chunk n = samples [shift*n, shift*n + chunk),
+ * shift = 16000/frame_hz, from a fresh model state), computed in two batched passes instead of N batch-1 steps:
+ * the conv stack over many chunks at once (chunks are convolved in isolation), the LSTM sequentially in time, then
+ * one transformer window per frame, max_batch windows per launch.  Does not touch any stream's state.
+ *   audio     : DEVICE pointer, planar [2][n_samples] fp32
+ *   out       : DEVICE pointer, [max_frames][6] fp32, same columns as vapb_step
+ *   n_frames  : HOST, receives the number of frames ((n_samples - chunk) / shift + 1)
+ * Synchronous (returns when `out` is complete).
+ */
+VAPB_API int vapb_score_offline(vapb_handle h, const float* audio, long long n_samples, float* out, long long max_frames,
+                       long long* n_frames, void* cuda_stream);
+
 /* Samples per channel per step: 16000/frame_hz + 320 (vap_main.py:230). */
 VAPB_API int vapb_chunk_samples(vapb_handle h);
 

@@ -183,3 +183,48 @@ def test_vap_queue_api_other_modes(fixture_audio, mode, hz, ctx, key):
             got = np.array(r["p_now"] + r["p_future"] + r["vad"])
         assert np.abs(got - want[:ncol]).max() < 1e-4
         assert len(r["x1"]) == shift
+
+
+def test_bulk_offline_scorer_head(tmp_path):
+    """vap_offline.run_bulk (vapb_score_offline): conv stack batched over chunks, LSTM sequential, one window per frame --
+    against the reference's own golden rows and against the frame-by-frame replay."""
+    from vap_realtime_b200 import vap_offline
+    from vap_realtime_b200.vap_main import VAPRealTime
+    d = np.load(os.path.join(GOLDEN, "ref_offline_head.npz"))
+    audio = d["audio"].astype(np.float32) / 32768.0
+    rows = d["golden_rows"]
+    vap = VAPRealTime(built_asset("vap_jp_20hz_2500msec.vapw"), None, torch.device("cuda"), 20, 2.5)
+    bulk = vap_offline.run_bulk(vap, audio[0], audio[1], max_batch=48)          # 120 frames: three window batches
+    step = vap_offline.run(vap, audio[0], audio[1])
+    assert len(bulk) == len(step) == len(rows)
+    b = np.array([[r["t"]] + r["p_now"] + r["p_future"] for r in bulk])
+    s = np.array([[r["t"]] + r["p_now"] + r["p_future"] for r in step])
+    assert np.allclose(b[:, 0], rows[:, 0])
+    print(f"bulk vs golden rows {np.abs(b[:, 1:] - rows[:, 1:]).max():.2e}, bulk vs frame-by-frame {np.abs(b - s).max():.2e}")
+    assert np.abs(b[:, 1:] - rows[:, 1:]).max() < 1e-4
+    assert np.abs(b - s).max() < 5e-5
+    out = tmp_path / "o.txt"
+    vap_offline.write_csv(str(out), bulk)
+    assert np.abs(np.loadtxt(out, delimiter=",", skiprows=1) - b).max() < 1e-9
+
+
+def test_bulk_offline_golden_full(vap_weights):
+    """All 5 312 rows of rvap/vap_main/output_offline.txt through the bulk scorer, with the GPU time it takes."""
+    import time
+    from vap_realtime_b200.engine import VapEngine
+    d = np.load(built_asset("jpn_pair_16k.npz"))
+    g = np.load(built_asset("golden_offline.npy"))
+    audio = torch.from_numpy(np.stack([d["left"], d["right"]]).astype(np.float32) / 32768.0).cuda()
+    eng = VapEngine(vap_weights, 20, 50, max_streams=256)
+    eng.set_option("gemm", 1)
+    eng.score_offline(audio[:, : 800 * 300 + 320])          # warm-up (module load, attribute calls)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = eng.score_offline(audio)
+    dt = time.perf_counter() - t0
+    assert out.shape[0] == len(g)
+    dd = np.abs(out[:, :4] - g[:, 1:])
+    print(f"bulk offline scorer: {len(g)} frames (265.7 s of dialogue) in {dt * 1e3:.0f} ms wall; max|d| vs output_offline.txt = {dd.max():.2e}, "
+          f"frames > 1e-5: {int((dd.max(1) > 1e-5).sum())}")
+    assert dd.max() < 1e-4
+    assert dt < 1.0

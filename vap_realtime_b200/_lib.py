@@ -19,6 +19,7 @@ SIGNATURES = {
     "vapb_reset_streams": (c_int, [c_void_p, POINTER(c_int), c_int]),
     "vapb_step": (c_int, [c_void_p, c_void_p, POINTER(c_int), c_int, c_void_p, c_void_p]),
     "vapb_step_host": (c_int, [c_void_p, c_void_p, POINTER(c_int), c_int, c_void_p, c_void_p]),
+    "vapb_score_offline": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_longlong, POINTER(ctypes.c_longlong), c_void_p]),
     "vapb_chunk_samples": (c_int, [c_void_p]),
     "vapb_state_floats": (c_size_t, [c_void_p]),
     "vapb_export_state": (c_int, [c_void_p, c_int, POINTER(c_float)]),

@@ -229,4 +229,10 @@ struct TailArgs {
 };
 void launch_tail(const TailArgs& a, cudaStream_t st);
 
+// ---- bulk offline scoring (vap_offline.py:51-73 over a whole file) ----
+// chunk rows, channel-major: dst[(ch * n_chunks + b)][0..S) = audio[ch][shift * (first + b) .. + S)
+void launch_make_chunks(const float* audio, long long n_samples, int shift, int S, long long first, int n_chunks, float* dst, cudaStream_t st);
+// X[(2b + ch) * T + j] = E[ch][f - t + 1 + j] for j < t = min(f + 1, T), f = first + b; zero rows above; tvalid[b] = t
+void launch_gather_windows(const float* E, long long n_frames, long long first, int B, int T, float* X, int* tvalid, int* ids_out, cudaStream_t st);
+
 }  // namespace vapb

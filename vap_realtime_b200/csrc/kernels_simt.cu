@@ -681,9 +681,11 @@ __global__ void __launch_bounds__(256) k_ln_gelu_ring(const float* __restrict__ 
     warp_norm8(v, 1.0f / 256.0f, w, b, lane);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-    const int id = ids[n >> 1], ch = n & 1;
-    const int slot = count[id] % T;
-    store_row8(ring + (((size_t)id * 2 + ch) * T + slot) * kD, lane, v);
+    if (ring) {
+        const int id = ids[n >> 1], ch = n & 1;
+        const int slot = count[id] % T;
+        store_row8(ring + (((size_t)id * 2 + ch) * T + slot) * kD, lane, v);
+    }
     if (e_out) store_row8(e_out + (size_t)n * kD, lane, v);
 }
 void launch_ln_gelu_ring(const float* X, int B, const float* w, const float* b, float* ring, const int* count,
@@ -1610,6 +1612,39 @@ void launch_tail(const TailArgs& a, cudaStream_t st) {
     static OncePerDevice once;
     if (once.first()) cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmem);
     launch_k(k_tail, dim3(kTailCluster * ((a.B + kTailStreams - 1) / kTailStreams)), dim3(256), kTailSmem, st, a);
+}
+
+// -----------------------------------------------------------------------------------------
+// Bulk offline scoring helpers (the reference replays a file frame by frame: vap_offline.py:51-73).
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_make_chunks(const float* __restrict__ audio, long long n_samples, int shift, int S, long long first,
+                                                     int n_chunks, float* __restrict__ dst) {
+    const int q = blockIdx.x;                       // chunk row = ch * n_chunks + b
+    const int ch = q / n_chunks, b = q - ch * n_chunks;
+    const float* src = audio + (size_t)ch * n_samples + (size_t)shift * (first + b);
+    float* d = dst + (size_t)q * S;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) d[i] = src[i];
+}
+void launch_make_chunks(const float* audio, long long n_samples, int shift, int S, long long first, int n_chunks, float* dst, cudaStream_t st) {
+    launch_k(k_make_chunks, dim3(2 * n_chunks), dim3(256), 0, st, audio, n_samples, shift, S, first, n_chunks, dst);
+}
+
+__global__ void __launch_bounds__(64) k_gather_windows(const float* __restrict__ E, long long n_frames, long long first, int B, int T,
+                                                       float* __restrict__ X, int* __restrict__ tvalid, int* __restrict__ ids_out) {
+    const int n = blockIdx.x;                       // sequence 2b + ch
+    const int b = n >> 1, ch = n & 1;
+    const long long f = first + b;
+    const int t = (int)((f + 1 < (long long)T) ? f + 1 : (long long)T);
+    const float4* src = reinterpret_cast<const float4*>(E + ((size_t)ch * n_frames + (size_t)(f - t + 1)) * kD);
+    float4* dst = reinterpret_cast<float4*>(X + (size_t)n * T * kD);
+    for (int i = threadIdx.x; i < T * 64; i += blockDim.x) dst[i] = (i < t * 64) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0 && ch == 0) {
+        tvalid[b] = t;
+        ids_out[b] = b;
+    }
+}
+void launch_gather_windows(const float* E, long long n_frames, long long first, int B, int T, float* X, int* tvalid, int* ids_out, cudaStream_t st) {
+    launch_k(k_gather_windows, dim3(2 * B), dim3(64), 0, st, E, n_frames, first, B, T, X, tvalid, ids_out);
 }
 
 }  // namespace vapb

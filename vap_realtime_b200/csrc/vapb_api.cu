@@ -103,6 +103,8 @@ struct vapb_ctx {
     // per-stream state
     float *hS = nullptr, *cS = nullptr, *ring = nullptr;
     int* count = nullptr;
+    int* bulk_ids = nullptr;         // device int = max_streams: the scratch LSTM slot of vapb_score_offline
+    int* bulk_count = nullptr;       // scratch frame counters for its window batches
 
     // layer-0 Q/K/V cache (batched path): LN(e_j) Wq / Wk / Wv of ar_channel depends on frame j only (no positional input,
     // ALiBi is a shift-invariant key bias: modules.py:93-95, 170-212), so it is projected once when the frame arrives and
@@ -768,13 +770,58 @@ void fused_transformer(Step& s) {
     mark(s, "fused_tf");
 }
 
-void enqueue_step(Step& s) {
+// ---- ar_channel + the three cross layers over X (window rows, oldest first) with the batched per-op kernels ----
+void transformer_batched(Step& s, bool prune, bool qkv_cached) {
     vapb_ctx* c = s.c;
-    vapb::g_use_pdl = c->opt_pdl != 0 && s.prof == nullptr;    // per-kernel event timing needs plain launches
-    vapb::g_attn_rk = c->opt_attn_rk != 0;
     const int B = s.B, NC = 2 * B, T = c->T;
     cudaStream_t st = s.st;
+    const size_t RX = (size_t)NC * T * kD;
+    tap_copy(s, c->tap_xin, c->X, RX);
+    // ---- ar_channel: one TransformerLayer per channel, shared weights (vap_main.py:285-286)
+    transformer_layer(s, c->layers[0], qkv_cached);
+    tap_copy(s, c->tap_chan, c->X, RX);
+    if (c->head_kind == VAPB_HEAD_VAP) {
+        launch_vad(c->X, c->tvalid, c->va_w, c->va_b, s.out, s.io, B, T, st); mark(s, "vad");
+    }
+    // ---- ar: three TransformerStereoLayers (modules.py:289-300, 395-423)
+    for (int li = 0; li < 3; ++li) {
+        if (li == 2 && prune) transformer_layer_last(s, c->layers[3], false, !c->opt_tail);
+        else transformer_layer(s, c->layers[1 + li]);
+        tap_copy(s, c->tap_cross[li], c->X, RX);
+    }
+}
 
+// ---- newest-frame side of the pruned layer (k_tail) or combinator + head; advances `count` of the batch's streams ----
+void tail_or_head(Step& s, bool prune, int* count) {
+    vapb_ctx* c = s.c;
+    const int B = s.B, T = c->T;
+    cudaStream_t st = s.st;
+    if (prune && c->opt_tail) {
+        const LayerWeights& lw = c->layers[3];
+        TailArgs t;
+        t.Xl = c->Xl; t.KVs = c->QKV; t.KVc = c->KVc; t.tvalid = c->tvalid;
+        t.WqT = c->t_WqT; t.WprojT = c->t_WprojT; t.WqcT = c->t_WqcT; t.WprojcT = c->t_WprojcT; t.W1T = c->t_W1T; t.W2T = c->t_W2T;
+        t.WaT = c->t_WaT; t.WbT = c->t_WbT; t.WhT = c->t_WhT;
+        t.ln_sa_w = lw.ln_sa_w; t.ln_sa_b = lw.ln_sa_b; t.ln_src_w = lw.ln_src_w; t.ln_src_b = lw.ln_src_b; t.ln_ff_w = lw.ln_ff_w; t.ln_ff_b = lw.ln_ff_b;
+        t.comb_lnw = c->comb_lnw; t.comb_lnb = c->comb_lnb; t.bh = c->bh; t.slopes_s = lw.sa.slopes; t.slopes_c = lw.slopes_c;
+        t.n_out = c->n_out; t.head_kind = c->head_kind; t.B = B; t.T = T;
+        t.out = s.out; t.io = s.io; t.count = count; t.ids = c->ids_dev;
+        launch_tail(t, st); mark(s, "tail");
+        return;
+    }
+    HeadArgs h;
+    h.X = prune ? c->Xl : c->X; h.compact = prune ? 1 : 0; h.tvalid = c->tvalid; h.Wa = c->Wa; h.Wb = c->Wb; h.lnw = c->comb_lnw; h.lnb = c->comb_lnb;
+    h.Wh = c->Wh; h.bh = c->bh; h.n_out = c->n_out; h.out = s.out; h.io = s.io;
+    h.comb_tap = c->opt_keep_taps ? c->tap_comb : nullptr;
+    h.logits_tap = c->opt_keep_taps ? c->tap_logits : nullptr;
+    h.count = count; h.ids = c->ids_dev; h.B = B; h.T = T; h.head_kind = c->head_kind;
+    launch_head(h, st); mark(s, "head");
+}
+
+// conv0 .. conv4 on NC chunk rows of s.audio, then the LSTM input projection of the inner frames -> c->Gx
+void encoder_convs(Step& s, int NC) {
+    vapb_ctx* c = s.c;
+    cudaStream_t st = s.st;
     // ---- CPC encoder on the newest chunk (encoder.py:58-80)
     launch_conv0(s.audio, s.io, NC, c->S, c->L[0], c->w0, c->b0, c->cn0w, c->cn0b, c->act[0], act_map(c, 0), st); mark(s, "conv0_cn_relu");
     for (int i = 0; i < 4; ++i) {
@@ -813,6 +860,21 @@ void enqueue_step(Step& s) {
         const RowMap g4 = plain_map(4 * kD);
         // input projection for all n_lstm frames at once (fp32), then the fused recurrence
         gemm(s, "gemm_lstm_x", c->act[4], am, c->Wih, c->opt_lstm_x_tc ? &c->tc_ih : nullptr, c->b_lstm, nullptr, g4, c->Gx, g4, NC * c->n_lstm, 4 * kD, kD, 0);
+    }
+}
+
+void transformer_batched(Step& s, bool prune, bool qkv_cached);
+void tail_or_head(Step& s, bool prune, int* count);
+
+void enqueue_step(Step& s) {
+    vapb_ctx* c = s.c;
+    vapb::g_use_pdl = c->opt_pdl != 0 && s.prof == nullptr;    // per-kernel event timing needs plain launches
+    vapb::g_attn_rk = c->opt_attn_rk != 0;
+    const int B = s.B, NC = 2 * B, T = c->T;
+    cudaStream_t st = s.st;
+    encoder_convs(s, NC);
+    {
+        const RowMap g4 = plain_map(4 * kD);
         if (c->opt_lstm_fused) {
             launch_lstm_recurrent(c->Gx, c->Whh, c->hS, c->cS, c->ids_dev, c->Y, NC, c->n_lstm, st); mark(s, "lstm_recurrent");
         } else {
@@ -859,45 +921,11 @@ void enqueue_step(Step& s) {
         else fused_transformer(s);
         transformer_layer_last(s, c->layers[3], true, !c->opt_tail);
     } else {
-    // ---- window of the last T embeddings, oldest first (vap_main.py:274-283)
-    launch_gather_ring(c->ring, c->count, c->ids_dev, c->X, c->tvalid, B, T, st); mark(s, "gather_ring");
-    const size_t RX = (size_t)NC * T * kD;
-    tap_copy(s, c->tap_xin, c->X, RX);
-    // ---- ar_channel: one TransformerLayer per channel, shared weights (vap_main.py:285-286)
-    transformer_layer(s, c->layers[0], qkv_cache_active(c));
-    tap_copy(s, c->tap_chan, c->X, RX);
-    if (c->head_kind == VAPB_HEAD_VAP) {
-        launch_vad(c->X, c->tvalid, c->va_w, c->va_b, s.out, s.io, B, T, st); mark(s, "vad");
+        // ---- window of the last T embeddings, oldest first (vap_main.py:274-283)
+        launch_gather_ring(c->ring, c->count, c->ids_dev, c->X, c->tvalid, B, T, st); mark(s, "gather_ring");
+        transformer_batched(s, prune, qkv_cache_active(c));
     }
-    // ---- ar: three TransformerStereoLayers (modules.py:289-300, 395-423)
-    for (int li = 0; li < 3; ++li) {
-        if (li == 2 && prune) transformer_layer_last(s, c->layers[3], false, !c->opt_tail);
-        else transformer_layer(s, c->layers[1 + li]);
-        tap_copy(s, c->tap_cross[li], c->X, RX);
-    }
-    }
-    if (prune && c->opt_tail) {
-        // ---- newest-frame side of the pruned layer + combinator + head + aggregation + frame counters: one kernel
-        const LayerWeights& lw = c->layers[3];
-        TailArgs t;
-        t.Xl = c->Xl; t.KVs = c->QKV; t.KVc = c->KVc; t.tvalid = c->tvalid;
-        t.WqT = c->t_WqT; t.WprojT = c->t_WprojT; t.WqcT = c->t_WqcT; t.WprojcT = c->t_WprojcT; t.W1T = c->t_W1T; t.W2T = c->t_W2T;
-        t.WaT = c->t_WaT; t.WbT = c->t_WbT; t.WhT = c->t_WhT;
-        t.ln_sa_w = lw.ln_sa_w; t.ln_sa_b = lw.ln_sa_b; t.ln_src_w = lw.ln_src_w; t.ln_src_b = lw.ln_src_b; t.ln_ff_w = lw.ln_ff_w; t.ln_ff_b = lw.ln_ff_b;
-        t.comb_lnw = c->comb_lnw; t.comb_lnb = c->comb_lnb; t.bh = c->bh; t.slopes_s = lw.sa.slopes; t.slopes_c = lw.slopes_c;
-        t.n_out = c->n_out; t.head_kind = c->head_kind; t.B = B; t.T = T;
-        t.out = s.out; t.io = s.io; t.count = c->count; t.ids = c->ids_dev;
-        launch_tail(t, st); mark(s, "tail");
-        return;
-    }
-    // ---- combinator + projection head + aggregation; advances the frame counters
-    HeadArgs h;
-    h.X = prune ? c->Xl : c->X; h.compact = prune ? 1 : 0; h.tvalid = c->tvalid; h.Wa = c->Wa; h.Wb = c->Wb; h.lnw = c->comb_lnw; h.lnb = c->comb_lnb;
-    h.Wh = c->Wh; h.bh = c->bh; h.n_out = c->n_out; h.out = s.out; h.io = s.io;
-    h.comb_tap = c->opt_keep_taps ? c->tap_comb : nullptr;
-    h.logits_tap = c->opt_keep_taps ? c->tap_logits : nullptr;
-    h.count = c->count; h.ids = c->ids_dev; h.B = B; h.T = T; h.head_kind = c->head_kind;
-    launch_head(h, st); mark(s, "head");
+    tail_or_head(s, prune, c->count);
 }
 
 // same decision as enqueue_step: does a batch of B run the per-stream cluster kernel (which recomputes layer 0)?
@@ -1082,8 +1110,10 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     const size_t MS = (size_t)max_streams, MB = (size_t)max_batch, NC = 2 * MB, R = NC * c->T;
     int rc = 0;
 #define DA(ptr, n) if (!rc) rc = dalloc(c, &(ptr), (n))
-    DA(c->hS, MS * 2 * kD);
-    DA(c->cS, MS * 2 * kD);
+    DA(c->hS, (MS + 1) * 2 * kD);      // + one scratch slot (index max_streams) for the bulk offline scorer
+    DA(c->cS, (MS + 1) * 2 * kD);
+    DA(c->bulk_ids, 1);
+    DA(c->bulk_count, MB);
     DA(c->ring, MS * 2 * c->T * kD);
     DA(c->count, MS);
     DA(c->iobuf_dev, sizeof(IoPtrs) + MB * sizeof(int));
@@ -1161,6 +1191,10 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
         if (!ok) FAIL_CREATE(VAPB_ECUDA, "tcgen05 setup failed: %s", terr.c_str());
     }
 
+    {
+        const int scratch = max_streams;
+        cudaMemcpy(c->bulk_ids, &scratch, sizeof(int), cudaMemcpyHostToDevice);
+    }
     c->h_cnt.assign(MS, 0);
     c->h_qkv.assign(MS, 0);
     if (build_fused_ops(c) != 0) FAIL_CREATE(VAPB_ECUDA, "%s", c->err.c_str());
@@ -1309,6 +1343,68 @@ int vapb_step_host(vapb_handle h, const float* audio, const int* ids, int B, flo
     if (rc) return rc;
     CK(h, cudaMemcpyAsync(out, h->out_stage, sizeof(float) * (size_t)B * 6, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
+    return VAPB_OK;
+}
+
+int vapb_score_offline(vapb_handle h, const float* audio, long long n_samples, float* out, long long max_frames, long long* n_frames,
+                       void* cuda_stream) {
+    if (!h) return VAPB_EINVAL;
+    if (!audio || !out || !n_frames) return fail(h, VAPB_EINVAL, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    vapb_ctx* c = h;
+    const int S = c->S, shift = S - kPadSamples, T = c->T, MB = c->max_batch;
+    const long long N = n_samples >= S ? (n_samples - S) / shift + 1 : 0;
+    *n_frames = N;
+    if (N == 0) return VAPB_OK;
+    if (N > max_frames) return fail(h, VAPB_EINVAL, "out holds %lld frames, the audio has %lld", max_frames, N);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) st = c->own_stream;
+    CK(h, cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    float* E = nullptr;                    // [2][N][256] embeddings of the whole file
+    if (cudaMalloc(&E, (size_t)2 * N * kD * sizeof(float)) != cudaSuccess) return fail(h, VAPB_ENOMEM, "cudaMalloc(embeddings) failed");
+    vapb::g_use_pdl = false;
+    vapb::g_attn_rk = c->opt_attn_rk != 0;
+    // ---- pass 1: encoder.  The conv stack treats every chunk in isolation (zero padding per chunk, encoder.py:58-80), so
+    // max_batch consecutive chunks of BOTH channels go through it as one batch; only the LSTM is sequential in time: one
+    // cluster walks n_lstm * Nc steps per channel with the state of a scratch slot that starts at zero (a fresh VAPRealTime).
+    CK(h, cudaMemsetAsync(c->hS + (size_t)c->max_streams * 2 * kD, 0, 2 * kD * sizeof(float), st));
+    CK(h, cudaMemsetAsync(c->cS + (size_t)c->max_streams * 2 * kD, 0, 2 * kD * sizeof(float), st));
+    for (long long b0 = 0; b0 < N; b0 += MB) {
+        const int Nc = (int)std::min<long long>(MB, N - b0);
+        launch_make_chunks(audio, n_samples, shift, S, b0, Nc, c->audio_stage, st);
+        Step s{c, st, Nc, c->audio_stage, nullptr};
+        encoder_convs(s, 2 * Nc);                                  // chunk rows are channel-major: row = ch * Nc + b
+        launch_lstm_recurrent(c->Gx, c->Whh, c->hS, c->cS, c->bulk_ids, c->Y, 2, c->n_lstm * Nc, st);
+        const int Kd = c->n_lstm * kD;
+        const int ks = (c->opt_gemm == 1 && c->opt_splitk) ? (Kd / 64) / 2 : 1;
+        const long long dstride = (long long)2 * Nc * kD;
+        if (ks > 1) {
+            gemm(s, "gemm_downsample", c->Y, plain_map(Kd), c->Wds, &c->tc_ds, c->bds, nullptr, plain_map(kD), c->part, plain_map(kD), 2 * Nc, kD, Kd, 0,
+                 nullptr, nullptr, ks, dstride, c->opt_conv4p);
+            launch_ln_gelu_ring(c->part, Nc, c->ds_lnw, c->ds_lnb, nullptr, nullptr, nullptr, T, c->ebuf, st, ks, dstride);
+        } else {
+            gemm(s, "gemm_downsample", c->Y, plain_map(Kd), c->Wds, &c->tc_ds, c->bds, nullptr, plain_map(kD), c->dsout, plain_map(kD), 2 * Nc, kD, Kd, 0);
+            launch_ln_gelu_ring(c->dsout, Nc, c->ds_lnw, c->ds_lnb, nullptr, nullptr, nullptr, T, c->ebuf, st);
+        }
+        for (int ch = 0; ch < 2; ++ch)
+            CK(h, cudaMemcpyAsync(E + ((size_t)ch * N + b0) * kD, c->ebuf + (size_t)ch * Nc * kD, (size_t)Nc * kD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    // ---- pass 2: the window of frame f is e[f-T+1 .. f]; windows are independent, so max_batch of them form one batch of
+    // the batched transformer kernels (last layer pruned to the newest frame, heads on the newest frame)
+    const bool prune = c->opt_prune && !c->opt_keep_taps;
+    for (long long f0 = 0; f0 < N; f0 += MB) {
+        const int Bw = (int)std::min<long long>(MB, N - f0);
+        launch_gather_windows(E, N, f0, Bw, T, c->X, c->tvalid, c->ids_dev, st);
+        Step s{c, st, Bw, nullptr, out + (size_t)f0 * 6};
+        transformer_batched(s, prune, false);
+        tail_or_head(s, prune, c->bulk_count);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(E);
+    h->last_B = 0;                          // ids_dev / tvalid were used as scratch
+    if (e != cudaSuccess) return fail(h, VAPB_ECUDA, "offline scoring failed: %s", cudaGetErrorString(e));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, VAPB_ECUDA, "offline scoring failed: %s", cudaGetErrorString(e));
     return VAPB_OK;
 }
 

@@ -46,6 +46,7 @@ class VapEngine:
         self.max_batch = int(max_batch or max_streams)
         self.head = head
         blob = _as_blob(weights)
+        self._weights_blob = blob          # kept so that a second engine (e.g. the bulk offline scorer) can share the weights
         self._h = ctypes.c_void_p()
         buf = ctypes.create_string_buffer(blob, len(blob))
         rc = self._lib.vapb_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), self.frame_hz, self.ctx_frames,
@@ -128,6 +129,26 @@ class VapEngine:
                                       ctypes.c_void_p(stream))
         _lib.check(rc, self._h)
         return out
+
+    def score_offline(self, audio):
+        """Bulk offline scoring of one recording (reference rvap/vap_main/vap_offline.py:51-73): audio [2, n_samples]
+        float32 (numpy array, CPU or CUDA tensor) -> numpy [n_frames, 6], identical in meaning to replaying the file
+        frame by frame from a fresh state.  Does not touch the state of any stream."""
+        torch = self._torch
+        a = torch.as_tensor(np.asarray(audio, dtype=np.float32) if not hasattr(audio, "data_ptr") else audio)
+        a = a.to(self._tdev, dtype=torch.float32).contiguous()
+        if a.dim() != 2 or a.shape[0] != 2:
+            raise ValueError("audio must be [2, n_samples]")
+        n = int(a.shape[1])
+        shift = self.chunk_samples - 320
+        n_frames = (n - self.chunk_samples) // shift + 1 if n >= self.chunk_samples else 0
+        out = torch.zeros((max(n_frames, 1), 6), dtype=torch.float32, device=self._tdev)
+        got = ctypes.c_longlong(0)
+        stream = torch.cuda.current_stream(self._tdev).cuda_stream
+        rc = self._lib.vapb_score_offline(self._h, ctypes.c_void_p(a.data_ptr()), n, ctypes.c_void_p(out.data_ptr()), n_frames,
+                                          ctypes.byref(got), ctypes.c_void_p(stream))
+        _lib.check(rc, self._h)
+        return out[: got.value].cpu().numpy()
 
     def profile_step(self, audio, ids: Optional[Sequence[int]] = None, out=None):
         """One eager step with an event behind every kernel -> {tag: (launches, ms)}."""

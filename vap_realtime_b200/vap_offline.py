@@ -29,6 +29,28 @@ def run(vap, data_left, data_right):
     return result
 
 
+def run_bulk(vap, data_left, data_right, max_batch: int = 256):
+    """Same result list as ``run`` for a whole recording, computed in bulk (``vapb_score_offline``): the conv stack
+    over many chunks at once, the LSTM sequentially, one transformer window per frame with ``max_batch`` windows per
+    launch -- instead of one batch-1 step per frame.  ``vap`` supplies the weights and the geometry; its own stream
+    state is not touched (the bulk pass starts from a fresh state like a new ``VAPRealTime``)."""
+    from .engine import VapEngine
+
+    eng = getattr(vap, "_bulk_engine", None)
+    if eng is None:
+        src = vap.engine
+        eng = VapEngine(src._weights_blob, frame_hz=vap.frame_rate, ctx_frames=vap.audio_context_len, max_streams=max_batch,
+                        head=src.head, device=src.device)
+        vap._bulk_engine = eng
+    n = min(len(data_left), len(data_right))
+    audio = np.stack([np.asarray(data_left[:n], dtype=np.float32), np.asarray(data_right[:n], dtype=np.float32)])
+    out = eng.score_offline(audio)
+    frame_size = vap.audio_frame_size
+    shift = frame_size - vap.frame_contxt_padding
+    return [{"t": float(shift * i + frame_size) / vap.sampling_rate, "p_now": [float(o[0]), float(o[1])], "p_future": [float(o[2]), float(o[3])]}
+            for i, o in enumerate(out)]
+
+
 def write_csv(path, result):
     with open(path, "w") as f:
         f.write("time_sec,p_now(0=left),p_now(1=right),p_future(0=left),p_future(1=right)\n")
@@ -50,9 +72,11 @@ def main(argv=None):
     p.add_argument("--vap_process_rate", type=int, default=20)
     p.add_argument("--context_len_sec", type=float, default=2.5)
     p.add_argument("--gpu", action="store_true")
+    p.add_argument("--frame_by_frame", action="store_true", help="replay with one process_vap call per frame (the reference's loop) instead of the bulk scorer")
     a = p.parse_args(argv)
     vap = VAPRealTime(a.vap_model, a.cpc_model, torch.device("cuda"), a.vap_process_rate, a.context_len_sec)
-    res = run(vap, read_wav_float32(a.input_wav_left), read_wav_float32(a.input_wav_right))
+    left, right = read_wav_float32(a.input_wav_left), read_wav_float32(a.input_wav_right)
+    res = run(vap, left, right) if a.frame_by_frame else run_bulk(vap, left, right)
     write_csv(a.filename_output, res)
     print("Generated output file: ", a.filename_output)
 
