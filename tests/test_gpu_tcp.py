@@ -81,7 +81,13 @@ def test_vap_main_server_over_tcp(fixture_audio):
     for p in range(n_frames * 5):                     # 160-sample packets, 10 ms of audio each
         in_sock.sendall(util.conv_2floatarray_2_bytearray(a[0, 160 * p: 160 * p + 160], a[1, 160 * p: 160 * p + 160]))
         if p % 5 == 4:
-            time.sleep(0.002)                         # let the poll-based broadcaster see every frame (it polls process_time_abs)
+            # Real clients send in real time (one frame per 50 ms).  Like the reference, the broadcaster snapshots the result
+            # attributes without a lock (vap_main.py:428-434) and process_vap overwrites current_x1_audio at its start
+            # (:258), so a replay faster than the broadcaster pairs p of frame n with the echo of frame n + 1: wait for
+            # result n before sending frame n + 1.
+            deadline = time.time() + 30
+            while len(results) < p // 5 + 1 and time.time() < deadline:
+                time.sleep(0.0005)
     reader.join(timeout=120)
     assert not reader.is_alive(), f"only {len(results)} of {n_frames} result packets arrived"
     in_sock.close()
