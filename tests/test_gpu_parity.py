@@ -122,22 +122,25 @@ def test_offline_golden_head(vap_weights):
     assert np.abs(out[:, :4] - rows[:, 1:]).max() < 1e-4
 
 
-@pytest.mark.parametrize("conv4p", [1, 3, 0])
-def test_offline_golden_full(vap_weights, conv4p):
+@pytest.mark.parametrize("conv4p,extra", [(1, {}), (3, {}), (0, {}), (1, {"lstm_x_tc": 1}), (1, {"fused_v": 2}), (1, {"tail": 0})])
+def test_offline_golden_full(vap_weights, conv4p, extra):
     """All 5312 rows of output_offline.txt through the tensor-core path (conv4p: with / without the
-    lo*lo product in the conv stack)."""
+    lo*lo product in the conv stack; extra: LSTM input projection on tcgen05, second-generation stream kernel,
+    per-op tail instead of k_tail)."""
     d = np.load(built_asset("jpn_pair_16k.npz"))
     g = np.load(built_asset("golden_offline.npy"))
     audio = torch.from_numpy(np.stack([d["left"], d["right"]]).astype(np.float32) / 32768.0).cuda()
     eng = VapEngine(vap_weights, 20, 50, max_streams=1)
     eng.set_option("gemm", DEF)
     eng.set_option("conv4p", conv4p)
+    for k, v in extra.items():
+        eng.set_option(k, v)
     outs = torch.empty((len(g), 6), device="cuda")
     for n in range(len(g)):
         eng.step(audio[None, :, 800 * n: 800 * n + 1120].contiguous(), out=outs[n:n + 1])
     out = outs.cpu().numpy()
     d = np.abs(out[:, :4] - g[:, 1:])
-    print(f"golden file (conv4p={conv4p}): max|d| =", d.max(), "frames > 1e-5:", int((d.max(1) > 1e-5).sum()))
+    print(f"golden file (conv4p={conv4p} {extra}): max|d| =", d.max(), "frames > 1e-5:", int((d.max(1) > 1e-5).sum()))
     assert d.max() < 1e-4
 
 
