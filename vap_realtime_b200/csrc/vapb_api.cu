@@ -87,7 +87,7 @@ struct vapb_ctx {
     ConvLayer conv[4];
     float *Wih = nullptr, *Whh = nullptr, *b_lstm = nullptr;
     TcWeight tc_ih;                  // W_ih planes: the LSTM input projection on tcgen05 (option lstm_x_tc); the recurrence stays fp32
-    int opt_lstm_x_tc = 0;
+    int opt_lstm_x_tc = 1;           // measured: -11 us per step at B = 64, golden file 1.73e-5 (fp32 projection: 1.97e-5)
     float *Wds = nullptr, *bds = nullptr, *ds_lnw = nullptr, *ds_lnb = nullptr;
     TcWeight tc_ds;
     LayerWeights layers[4];          // [0] = ar_channel.layers.0, [1..3] = ar.layers.0..2
