@@ -122,10 +122,10 @@ def test_offline_golden_head(vap_weights):
     assert np.abs(out[:, :4] - rows[:, 1:]).max() < 1e-4
 
 
-@pytest.mark.parametrize("conv4p,extra", [(1, {}), (3, {}), (0, {}), (1, {"lstm_x_tc": 1}), (1, {"fused_v": 2}), (1, {"tail": 0})])
+@pytest.mark.parametrize("conv4p,extra", [(1, {}), (3, {}), (0, {}), (1, {"lstm_x_tc": 0}), (1, {"fused_v": 1}), (1, {"tail": 0})])
 def test_offline_golden_full(vap_weights, conv4p, extra):
     """All 5312 rows of output_offline.txt through the tensor-core path (conv4p: with / without the
-    lo*lo product in the conv stack; extra: LSTM input projection on tcgen05, second-generation stream kernel,
+    lo*lo product in the conv stack; extra: fp32 LSTM input projection, first-generation stream kernel,
     per-op tail instead of k_tail)."""
     d = np.load(built_asset("jpn_pair_16k.npz"))
     g = np.load(built_asset("golden_offline.npy"))
@@ -182,7 +182,7 @@ def test_option_variants_agree(vap_weights, fixture_audio):
     audio, ref = fixture_audio
     outs = {}
     for name, opts in {"default": {}, "lstm_unfused": {"lstm_fused": 0}, "tile64": {"tile_n": 64},
-                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}, "ln_unfused": {"fuse_ln": 0}, "no_k256": {"k256": 0}, "pdl": {"pdl": 1}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "no_fused": {"fused": 0}, "stream_v2": {"fused_v": 2}, "no_tail": {"tail": 0}}.items():
+                       "tile128": {"tile_n": 128}, "tile256": {"tile_n": 256}, "ln_unfused": {"fuse_ln": 0}, "no_k256": {"k256": 0}, "pdl": {"pdl": 1}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "no_fused": {"fused": 0}, "stream_v1": {"fused_v": 1}, "no_tail": {"tail": 0}}.items():
         eng = VapEngine(vap_weights, 20, 50, max_streams=3)
         eng.set_option("gemm", DEF)
         for k, v in opts.items():

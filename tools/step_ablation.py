@@ -11,7 +11,9 @@ w, _ = bench.load_weights("vap")
 audio = torch.from_numpy(bench.make_audio(B, 8)).cuda()
 configs = {"default": {}, "no_fused": {"fused": 0}, "pdl": {"pdl": 1}, "no_k256": {"k256": 0}, "no_prune": {"prune": 0}, "attn_rk": {"attn_rk": 1}, "fork": {"fork": 1}, "no_splitk": {"splitk": 0}, "cluster2": {"cluster2": 1}, "conv4p_0": {"conv4p": 0}, "conv4p_3": {"conv4p": 3},
            "ln_unfused": {"fuse_ln": 0}, "lstm_unfused": {"lstm_fused": 0}, "gemm_fp32": {"gemm": 0},
-           "no_tail": {"tail": 0}, "stream_v2": {"fused_v": 2}, "lstm_x_tc": {"lstm_x_tc": 1}}
+           "no_tail": {"tail": 0}, "stream_v2": {"fused_v": 2}, "lstm_x_tc": {"lstm_x_tc": 1},
+           "no_lstm_x_tc": {"lstm_x_tc": 0}, "conv1_ks2": {"conv12_ks": 0x02}, "conv12_ks2": {"conv12_ks": 0x22}, "conv1_ks4": {"conv12_ks": 0x04},
+           "v2_conv1_ks2": {"fused_v": 2, "conv12_ks": 0x02}}
 only = [x for x in os.environ.get("ONLY", "").split(",") if x]
 for name, opts in configs.items():
     if only and name not in only:

@@ -98,6 +98,7 @@ struct vapb_ctx {
     float *t_WqT = nullptr, *t_WprojT = nullptr, *t_WqcT = nullptr, *t_WprojcT = nullptr, *t_W1T = nullptr, *t_W2T = nullptr,
           *t_WaT = nullptr, *t_WbT = nullptr, *t_WhT = nullptr;
     int opt_tail = 1;                // 1 = k_tail (one kernel), 0 = the nine per-op kernels
+    int opt_conv12_ks = 0;           // experiment: split-K of conv1 (low nibble) and conv2 (high nibble); 0 = none
     float *va_w = nullptr, *va_b = nullptr;
 
     // per-stream state
@@ -148,7 +149,7 @@ struct vapb_ctx {
                   *Qc2l = nullptr, *H2h = nullptr, *H2l = nullptr;
     F2Op* f2ops = nullptr;
     int n_f2ops = 0;
-    int opt_fused_v = 1;             // 1 = first-generation stream kernel (default: measured equal or faster), 2 = second generation where it applies (T <= 64)
+    int opt_fused_v = 2;             // 2 = second-generation stream kernel where it applies (T <= 64; measured 581 vs 597 us per step at B = 64), 1 = first generation
     const float* fused_ds_part = nullptr;      // downsample partials handed to the stream kernel (its gather op finishes the embedding)
     long long fused_ds_stride = 0;
     int fused_ds_nsplit = 0;
@@ -837,7 +838,7 @@ void encoder_convs(Step& s, int NC) {
         const int Mc = NC * cv.Lout;
         // split-K factors are fixed per layer (conv3: 2, conv4: 4) so that a stream's arithmetic does not depend
         // on the batch size; shorter accumulation chains + fp32 summation also measurably help parity
-        const int ks_layer[4] = {1, 1, 2, 4};
+        const int ks_layer[4] = {c->opt_conv12_ks & 0xf ? (c->opt_conv12_ks & 0xf) : 1, (c->opt_conv12_ks >> 4) ? (c->opt_conv12_ks >> 4) : 1, 2, 4};
         const int ks = (c->opt_gemm == 1 && c->opt_splitk && (size_t)Mc * kD <= c->part_stride) ? ks_layer[i] : 1;
         if (ks > 1) {
             // small M, long K: K is split over CTAs; ChannelNorm sums the partial products
@@ -1133,7 +1134,7 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     DA(c->Hd, R * kFF);
     DA(c->KVc, R * 2 * kD);
     DA(c->Qc, R * kD);
-    c->part_stride = NC * (size_t)c->L[3] * kD;          // largest split-K user: conv3 output rows
+    c->part_stride = NC * (size_t)c->L[1] * kD;          // largest possible split-K user: conv1 output rows (option conv12_ks)
     DA(c->part, 4 * c->part_stride + 20 * NC * kD);      // conv3/conv4 use <= 4 slabs; the downsample up to 20 tiny ones
     DA(c->Xl, NC * kD);
     DA(c->Zl, NC * kD);
@@ -1472,7 +1473,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v" || k == "tail" || k == "lstm_x_tc" || k == "qkv_cache") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v" || k == "tail" || k == "lstm_x_tc" || k == "qkv_cache" || k == "conv12_ks") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -1494,6 +1495,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "tail") h->opt_tail = value ? 1 : 0;
         else if (k == "lstm_x_tc") h->opt_lstm_x_tc = value ? 1 : 0;
         else if (k == "qkv_cache") h->opt_qkv_cache = value ? 1 : 0;
+        else if (k == "conv12_ks") h->opt_conv12_ks = value & 0xff;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -1533,6 +1535,7 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "tail") *value = h->opt_tail;
     else if (k == "lstm_x_tc") *value = h->opt_lstm_x_tc;
     else if (k == "qkv_cache") *value = h->opt_qkv_cache;
+    else if (k == "conv12_ks") *value = h->opt_conv12_ks;
     else if (k == "fused_v") *value = (h->opt_fused_v == 2 && h->f2ops) ? 2 : 1;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
