@@ -463,8 +463,11 @@ def run_ours(args):
                     tsrc = "profiles/" + os.path.basename(tp) + " (" + tj["source"] + ")"
             if dom["kind"] == "stream":
                 fl = B * stream_kernel_gflop_per_frame(T) * 1e9
-                name = ("k_stream_tf: per-stream persistent transformer kernel (ring gather, ar_channel layer, vad, cross layers 0-1, "
-                        "K/V of the pruned last layer; tcgen05 bf16x3 GEMMs + tensor-core attention), one launch per step")
+                gen = eng.get_option("fused_v")
+                name = (("k_stream_tf2 (second generation: clusters of four CTAs = two streams, TMA-fed multicast operands, LayerNorm folded "
+                         "into the epilogue)" if gen == 2 else "k_stream_tf (first generation: a cluster of two CTAs per stream, A operand in tensor memory)")
+                        + ": per-stream persistent transformer kernel (ring gather, ar_channel layer, vad, cross layers 0-1, K/V of the "
+                          "pruned last layer; tcgen05 bf16x3 GEMMs + tensor-core attention), one launch per step")
                 pk, pk_src = peak, peak_src            # timed inside the step: sustained figure
             else:
                 fl = 2.0 * dom["M"] * dom["N"] * dom["K"]
