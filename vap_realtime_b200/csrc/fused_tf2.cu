@@ -158,23 +158,32 @@ __device__ __forceinline__ void stg_put_co(uint32_t stg, int lane, int i, uint4 
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_addr(stg, 4 * i + (lane >> 3), lane & 7)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
-// staging tile -> 32 global rows of 128 bytes at `base + row * pitch` (bytes)
-template <bool PLANE = false>
-__device__ __forceinline__ void stg_store_rows(uint32_t stg, int lane, uint8_t* base, size_t pitch) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint4 v = stg_get_co(stg, lane, i);
-        if (PLANE) { F2_STORE_P(st_global_v4(base + (size_t)(4 * i + (lane >> 3)) * pitch + (lane & 7) * 16, v.x, v.y, v.z, v.w);) }
-        else { F2_STORE(st_global_v4(base + (size_t)(4 * i + (lane >> 3)) * pitch + (lane & 7) * 16, v.x, v.y, v.z, v.w);) }
+// staging tile (32 rows x 128 bytes, exactly the SWIZZLE_128B box layout) -> global through ONE TMA store issued by lane 0.
+// The LSU never sees these bytes: thread-per-row st.global made the first cut of this kernel slower than its predecessor,
+// coalesced st.global through the tile still cost ~150 k cycles per launch (timing-only builds without the stores).
+// Returns when the tile may be rewritten (the TMA engine has read it); completion of the writes is awaited once per op.
+template <bool PLANE>
+__device__ __forceinline__ void stg_tma_store_2d(uint32_t stg, int lane, const CUtensorMap* map, int c0, int c1) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        if (PLANE) { F2_STORE_P(tma_store_2d(map, c0, c1, stg);) } else { F2_STORE(tma_store_2d(map, c0, c1, stg);) }
+        tma_store_commit();
+        tma_store_wait_read();
     }
+    __syncwarp();
 }
-// a thread's 64 packed bf16 pairs (= 64 columns... 32 words = 128 bytes of one plane row) through the staging tile to global
-__device__ __forceinline__ void store_plane_rows(uint32_t stg, int lane, const uint32_t* w, __nv_bfloat16* base, size_t ld) {
+// a thread's 64 packed bf16 pairs (32 words = the 128 bytes of one plane row) -> plane rows [row0, row0 + 32), columns [col, col + 64)
+__device__ __forceinline__ void store_plane_rows(uint32_t stg, int lane, const uint32_t* w, const CUtensorMap* map, int col, int row0) {
     stg_put_row(stg, lane, w);
-    __syncwarp();
-    stg_store_rows<true>(stg, lane, reinterpret_cast<uint8_t*>(base), ld * 2);
+    stg_tma_store_2d<true>(stg, lane, map, col, row0);
+}
+// end of an op: every store this warp issued is complete before the op barrier publishes the results
+__device__ __forceinline__ void stores_done(int lane) {
+    if (lane == 0) tma_store_wait_all();
     __syncwarp();
 }
+
 // mean and M2 (sum of squared deviations) of 32 values, two passes in registers
 __device__ __forceinline__ float2 block_stats32(const float (&v)[32]) {
     float s0 = 0.f, s1 = 0.f;
@@ -240,10 +249,10 @@ __device__ __forceinline__ void load_acc_block(const Ctx2& c, uint32_t taddr, in
 }
 
 // planes out (+ LayerNorm correction, + GELU): one 128-byte row per thread and plane through the staging tile
-__device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
+__device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, const F2Fields& op, const Fused2Params& p, int gs) {
     const int q = c.warp & 3, hf = c.warp >> 2;
     const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
-    const size_t grow0 = (size_t)c.b * 128 + 32 * q;
+    const int grow0 = c.b * 128 + 32 * q;
     const int ns = op.N >> 8;
     const uint32_t tm_row = c.tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = c.stg();
@@ -270,23 +279,24 @@ __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Fields& op, 
 #pragma unroll
             for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[16 * blk + e], L[16 * blk + e]);
         }
-        store_plane_rows(stg, c.lane, H, op.out_hi + grow0 * op.ld_out + col0, op.ld_out);
-        store_plane_rows(stg, c.lane, L, op.out_lo + grow0 * op.ld_out + col0, op.ld_out);
+        store_plane_rows(stg, c.lane, H, &gop->m[4], col0, grow0);
+        store_plane_rows(stg, c.lane, L, &gop->m[5], col0, grow0);
     }
+    stores_done(c.lane);
     if (fine) fine[3] = clock64();
 }
 
 // X update: x += acc (residual), fp32 rows + planes + LayerNorm block statistics.  The residual block is fetched coalesced
-// one block ahead and passes through the staging tile to reach the thread that owns the row.
-__device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
+// one block ahead and passes through the staging tile to reach the thread that owns the row; results leave through TMA.
+__device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Op* gop, const F2Fields& op, const Fused2Params& p, int gs) {
     const int q = c.warp & 3, hf = c.warp >> 2;
     const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
-    const size_t grow0 = (size_t)c.b * 128 + 32 * q;
+    const int grow0 = c.b * 128 + 32 * q;
     const int ns = op.N >> 8;
     const uint32_t tm_row = c.tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = c.stg();
     long long* fine = c.tid == 0 ? c.fine : nullptr;
-    auto res_ptr = [&](int col, int i) { return reinterpret_cast<const uint4*>(p.Xf + (grow0 + 4 * i + (c.lane >> 3)) * kD + col + 4 * (c.lane & 7)); };
+    auto res_ptr = [&](int col, int i) { return reinterpret_cast<const uint4*>(p.Xf + ((size_t)grow0 + 4 * i + (c.lane >> 3)) * kD + col + 4 * (c.lane & 7)); };
     for (int s = 0; s < ns; ++s) {
         const int g = gs + s, slot = g & (kAcc - 1);
         const int col0 = 256 * s + 128 * c.r + 64 * hf;
@@ -297,6 +307,7 @@ __device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Fields& op, const
         tc_fence_after();
         if (fine && s == 0) fine[1] = clock64();
         if (fine && s == ns - 1) fine[2] = clock64();
+        uint32_t H[32], L[32];
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
             const int col = col0 + 32 * blk;
@@ -324,33 +335,19 @@ __device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Fields& op, const
                 for (int e = 0; e < 32; ++e) vb[e] = __float_as_uint(v[e]);
                 stg_put_row(stg, c.lane, vb);
             }
-            __syncwarp();
-            stg_store_rows(stg, c.lane, reinterpret_cast<uint8_t*>(p.Xf + grow0 * kD + col), kD * 4);
-            __syncwarp();
-            // planes of this block: 64 bytes hi | 64 bytes lo per row in one staging tile
-            {
-                uint32_t hl[32];
+            stg_tma_store_2d<false>(stg, c.lane, &gop->m[6], col, grow0);          // fp32 residual stream
 #pragma unroll
-                for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], hl[e], hl[16 + e]);
-                stg_put_row(stg, c.lane, hl);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                // pass i: rows 4i .. 4i + 3; lanes 0-3 of a row's group carry hi, lanes 4-7 lo
-                const uint4 x4 = stg_get_co(stg, c.lane, i);
-                const int rr = 4 * i + (c.lane >> 3), ch = c.lane & 7;
-                __nv_bfloat16* dst = (ch < 4 ? p.Xh : p.Xl) + (grow0 + rr) * kD + col + 8 * (ch & 3);
-                F2_STORE_P(st_global_v4(dst, x4.x, x4.y, x4.z, x4.w);)
-            }
-            __syncwarp();
+            for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[16 * blk + e], L[16 * blk + e]);
         }
+        store_plane_rows(stg, c.lane, H, &gop->m[4], col0, grow0);
+        store_plane_rows(stg, c.lane, L, &gop->m[5], col0, grow0);
     }
+    stores_done(c.lane);
     if (fine) fine[3] = clock64();
 }
 
 // fp32 rows in the batched kernels' layout (K / V of the pruned layer for the newest-frame tail)
-__device__ __noinline__ void epilogue_f32(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
+__device__ __noinline__ void epilogue_f32(const Ctx2& c, const F2Op* gop, const F2Fields& op, const Fused2Params& p, int gs) {
     const int q = c.warp & 3, hf = c.warp >> 2;
     const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
     const int ns = op.N >> 8;
@@ -376,26 +373,29 @@ __device__ __noinline__ void epilogue_f32(const Ctx2& c, const F2Fields& op, con
 #pragma unroll
             for (int e = 0; e < 32; ++e) vb[e] = __float_as_uint(v[e]);
             stg_put_row(stg, c.lane, vb);
-            __syncwarp();
-            float* dst = (col < 512 ? op.out_f : op.out_f2) + (col & 511);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = 32 * q + 4 * i + (c.lane >> 3);
-                const int seq = rr >> 6, pos = rr & 63;
-                const uint4 x4 = stg_get_co(stg, c.lane, i);
-                if (pos < c.T && !c.ghost) { F2_STORE(st_global_v4(dst + ((size_t)(2 * c.b + seq) * c.T + pos) * 512 + 4 * (c.lane & 7), x4.x, x4.y, x4.z, x4.w);) }
+            // rows 32q .. 32q + 31 of the tile = positions 32 (q & 1) .. + 31 of sequence q >> 1; positions >= T are clipped by the map
+            if (!c.ghost) {
+                fence_proxy_async();
+                __syncwarp();
+                if (c.lane == 0) {
+                    F2_STORE(tma_store_3d(&gop->m[col < 512 ? 4 : 5], col & 511, 32 * (q & 1), 2 * c.b + (q >> 1), stg);)
+                    tma_store_commit();
+                    tma_store_wait_read();
+                }
             }
             __syncwarp();
         }
     }
+    stores_done(c.lane);
     if (fine) fine[3] = clock64();
 }
 
 __device__ __forceinline__ void gemm_epilogue(const Ctx2& c, const F2Fields& op, const Fused2Params& p, int gs) {
     const int mode = __shfl_sync(0xffffffffu, op.out_mode, 0);
-    if (mode == F2_OUT_PLANES) epilogue_planes(c, op, p, gs);
-    else if (mode == F2_OUT_X) epilogue_x(c, op, p, gs);
-    else epilogue_f32(c, op, p, gs);
+    const F2Op* gop = &p.ops[c.oi];
+    if (mode == F2_OUT_PLANES) epilogue_planes(c, gop, op, p, gs);
+    else if (mode == F2_OUT_X) epilogue_x(c, gop, op, p, gs);
+    else epilogue_f32(c, gop, op, p, gs);
 }
 
 // ============================== GEMM: tile schedule ==============================
@@ -595,7 +595,7 @@ __device__ __forceinline__ void attn_mma(const Ctx2& c, int at, int wt, int na) 
     for (int x = 0; x < 2; ++x) umma_commit_mc(c.w_empty((wt + 2 + x) % kWStg), c.mask_w);
 }
 
-__device__ __noinline__ void attn_workers(const Ctx2& c, const F2Fields& op, int na) {
+__device__ __noinline__ void attn_workers(const Ctx2& c, const F2Op* gop, const F2Fields& op, int na) {
     const int q = c.warp & 3, x = c.warp >> 2;             // quadrant q of head x
     const uint32_t par = (uint32_t)na & 1u;
     const uint32_t tm_q = c.tmem_base + ((uint32_t)(q * 32) << 16);
@@ -667,9 +667,10 @@ __device__ __noinline__ void attn_workers(const Ctx2& c, const F2Fields& op, int
         for (int e = 0; e < 16; ++e) split2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1]), H[16 * half + e], L[16 * half + e]);
     }
     tc_fence_before();
-    const size_t grow0 = (size_t)c.b * 128 + 32 * q;
-    store_plane_rows(c.stg(), c.lane, H, op.out_hi + grow0 * op.ld_out + head * 64, op.ld_out);
-    store_plane_rows(c.stg(), c.lane, L, op.out_lo + grow0 * op.ld_out + head * 64, op.ld_out);
+    const int grow0 = c.b * 128 + 32 * q;
+    store_plane_rows(c.stg(), c.lane, H, &gop->m[4], head * 64, grow0);
+    store_plane_rows(c.stg(), c.lane, L, &gop->m[5], head * 64, grow0);
+    stores_done(c.lane);
 }
 
 // ============================== ring gather (+ downsample tail) ==============================
@@ -881,7 +882,7 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
             if (c.fine && c.tid == 0) c.fine[0] = clock64();
             if (c.warp < kWorkers2) {
                 if (kind == F2_GEMM) gemm_epilogue(c, op, p, gs);
-                else if (kind == F2_ATTN) attn_workers(c, op, na);
+                else if (kind == F2_ATTN) attn_workers(c, &p.ops[oi], op, na);
                 else gather_op(c, p, id, cnt);
             } else if (c.warp == kWorkers2 + 1) {
                 if (oi + 1 < p.n_ops)        // fields of the next op -> the other shared-memory slot (visible after the op barrier)

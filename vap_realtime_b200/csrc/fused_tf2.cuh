@@ -56,10 +56,13 @@ struct alignas(64) F2Op {
     // GEMM: m[0] / m[1] = A hi / lo planes (box 64 rows x 64: each CTA of a stream multicasts half a tile),
     //       m[2] / m[3] = W hi / lo (box 64 n x 64 k: each CTA of a column half multicasts half a tile)
     // ATTN: m[0] / m[1] = Q planes (box 128 rows x 64), m[2] / m[3] = K / V planes (box 64 rows x 64)
-    CUtensorMap m[4];
+    // every op: m[4] / m[5] = output hi / lo planes (box 32 rows x 64 columns, TMA stores out of the epilogue staging tiles);
+    //           F2_OUT_X: the X planes, m[6] = the fp32 residual stream (box 32 rows x 32 floats);
+    //           F2_OUT_F32: m[4] / m[5] = fp32 [sequence][position][512] tensors of out_f / out_f2 (box 32 x 32 x 1: positions >= T are clipped)
+    CUtensorMap m[7];
     F2Fields f;
 };
-static_assert(sizeof(F2Fields) == 128 && sizeof(F2Op) == 640, "F2Op layout");
+static_assert(sizeof(F2Fields) == 128 && sizeof(F2Op) == 1024, "F2Op layout");
 
 struct Fused2Params {
     const F2Op* ops;

@@ -640,6 +640,37 @@ bool tc_encode_bf16_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, in
     return encode_plane(map, ptr, (int)rows, (int)cols, box_rows, err);
 }
 
+bool tc_encode_f32_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err) {
+    EncodeTiledFn fn = get_encode_fn(err);
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        err = "cuTensorMapEncodeTiled (fp32 2d) failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+bool tc_encode_f32_3d(CUtensorMap* map, void* ptr, size_t d2, size_t d1, size_t cols, int box_d1, std::string& err) {
+    EncodeTiledFn fn = get_encode_fn(err);
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)d1, (cuuint64_t)d2};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * d1};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)box_d1, 1u};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        err = "cuTensorMapEncodeTiled (fp32 3d) failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
 bool tc_prepare_weight(const float* W_dev, int N, int K, TcWeight& out, std::vector<void*>& allocs, std::string& err) {
     if (!W_dev) {
         err = "tc_prepare_weight: null weight";

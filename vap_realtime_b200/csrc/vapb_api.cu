@@ -671,22 +671,30 @@ int build_fused2(vapb_ctx* c) {
     DA2(c->H2l, R2 * kFF);
 #undef DA2
     if (rc) return rc;
-    struct Planes { CUtensorMap hi128, lo128, hi64, lo64; };
+    struct Planes { CUtensorMap hi128, lo128, hi64, lo64, hi32, lo32; };      // box rows 128 / 64 (loads) and 32 (epilogue stores)
     auto planes = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, size_t cols, Planes& m) {
         return tc_encode_bf16_2d(&m.hi128, hi, R2, cols, 128, err) && tc_encode_bf16_2d(&m.lo128, lo, R2, cols, 128, err) &&
-               tc_encode_bf16_2d(&m.hi64, hi, R2, cols, 64, err) && tc_encode_bf16_2d(&m.lo64, lo, R2, cols, 64, err);
+               tc_encode_bf16_2d(&m.hi64, hi, R2, cols, 64, err) && tc_encode_bf16_2d(&m.lo64, lo, R2, cols, 64, err) &&
+               tc_encode_bf16_2d(&m.hi32, hi, R2, cols, 32, err) && tc_encode_bf16_2d(&m.lo32, lo, R2, cols, 32, err);
     };
     Planes mX, mG1, mO, mQc, mH;
     if (!planes(c->X2h, c->X2l, kD, mX) || !planes(c->G1h, c->G1l, 1280, mG1) || !planes(c->O2h, c->O2l, kD, mO) ||
         !planes(c->Qc2h, c->Qc2l, kD, mQc) || !planes(c->H2h, c->H2l, kFF, mH))
         return fail(c, VAPB_ECUDA, "stream kernel v2 tensor maps: %s", err.c_str());
+    CUtensorMap mXf, mKVs, mKVc;           // fp32 store targets: residual stream; K | V rows of the pruned layer for the tail
+    if (!tc_encode_f32_2d(&mXf, c->X2f, R2, kD, 32, err) || !tc_encode_f32_3d(&mKVs, c->QKV, (size_t)2 * c->max_batch, c->T, 512, 32, err) ||
+        !tc_encode_f32_3d(&mKVc, c->KVc, (size_t)2 * c->max_batch, c->T, 512, 32, err))
+        return fail(c, VAPB_ECUDA, "stream kernel v2 tensor maps: %s", err.c_str());
 
     std::vector<F2Op> ops;
     auto gemm = [&](const Planes& A, int K, const TcWeight& w, int N, int out_mode, int n_ln, const float* ls, const float* lc, int act,
-                    __nv_bfloat16* oh, __nv_bfloat16* ol, int ld_out, int cta_sync) {
+                    const Planes* out, __nv_bfloat16* oh, __nv_bfloat16* ol, int ld_out, int cta_sync) {
         F2Op o;
         memset(&o, 0, sizeof o);
         o.m[0] = A.hi64; o.m[1] = A.lo64; o.m[2] = w.map_hi[0]; o.m[3] = w.map_lo[0];
+        if (out_mode == F2_OUT_X) { o.m[4] = mX.hi32; o.m[5] = mX.lo32; o.m[6] = mXf; }
+        else if (out_mode == F2_OUT_F32) { o.m[4] = mKVs; o.m[5] = mKVc; }
+        else { o.m[4] = out->hi32; o.m[5] = out->lo32; }
         o.f.kind = F2_GEMM; o.f.K = K; o.f.N = N; o.f.out_mode = out_mode; o.f.n_ln = n_ln; o.f.ln_s = ls; o.f.ln_c = lc; o.f.act = act;
         o.f.out_hi = oh; o.f.out_lo = ol; o.f.ld_out = ld_out; o.f.cta_sync = cta_sync;
         ops.push_back(o);
@@ -694,7 +702,7 @@ int build_fused2(vapb_ctx* c) {
     auto attn = [&](const Planes& Q, int qcol, int kcol, int vcol, const float* slopes, int sibling) {
         F2Op o;
         memset(&o, 0, sizeof o);
-        o.m[0] = Q.hi128; o.m[1] = Q.lo128; o.m[2] = mG1.hi64; o.m[3] = mG1.lo64;
+        o.m[0] = Q.hi128; o.m[1] = Q.lo128; o.m[2] = mG1.hi64; o.m[3] = mG1.lo64; o.m[4] = mO.hi32; o.m[5] = mO.lo32;
         o.f.kind = F2_ATTN; o.f.qcol = qcol; o.f.kcol = kcol; o.f.vcol = vcol; o.f.slopes = slopes; o.f.sibling = sibling;
         o.f.out_hi = c->O2h; o.f.out_lo = c->O2l; o.f.ld_out = kD;
         ops.push_back(o);
@@ -709,21 +717,21 @@ int build_fused2(vapb_ctx* c) {
         const LayerWeights& lw = c->layers[l];
         const vapb_ctx::V2Layer& v = c->v2[l];
         // Q / K / V of the self attention (LayerNorm folded) [+ K / V of the cross attention from the raw rows]: one op
-        gemm(mX, kD, v.g1, v.n_g1, F2_OUT_PLANES, v.nln_g1, v.s_g1, v.c_g1, 0, c->G1h, c->G1l, 1280, 1);
+        gemm(mX, kD, v.g1, v.n_g1, F2_OUT_PLANES, v.nln_g1, v.s_g1, v.c_g1, 0, &mG1, c->G1h, c->G1l, 1280, 1);
         if (l == 1 && c->head_kind == VAPB_HEAD_VAP) ops.back().f.side = F2_SIDE_VAD;      // reads the ar_channel output
         attn(mG1, 0, 256, 512, lw.sa.slopes, 0);
-        gemm(mO, kD, lw.sa.tc_proj, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, kD, 0);
+        gemm(mO, kD, lw.sa.tc_proj, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, kD, 0);
         if (lw.cross) {
-            gemm(mX, kD, v.qc, kD, F2_OUT_PLANES, kD, v.s_qc, v.c_qc, 0, c->Qc2h, c->Qc2l, kD, 1);
+            gemm(mX, kD, v.qc, kD, F2_OUT_PLANES, kD, v.s_qc, v.c_qc, 0, &mQc, c->Qc2h, c->Qc2l, kD, 1);
             attn(mQc, 0, 768, 1024, lw.slopes_c, 1);
-            gemm(mO, kD, lw.tc_proj_c, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, kD, 0);
+            gemm(mO, kD, lw.tc_proj_c, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, kD, 0);
         }
-        gemm(mX, kD, v.w1, kFF, F2_OUT_PLANES, kFF, v.s_1, v.c_1, 1, c->H2h, c->H2l, kFF, 0);
-        gemm(mH, kFF, lw.tc_w2, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, kD, 0);
+        gemm(mX, kD, v.w1, kFF, F2_OUT_PLANES, kFF, v.s_1, v.c_1, 1, &mH, c->H2h, c->H2l, kFF, 0);
+        gemm(mH, kFF, lw.tc_w2, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, kD, 0);
     }
     {   // pruned last layer: window-wide K / V (self: LayerNorm folded, cross: raw rows) as fp32 rows for the newest-frame tail
         const vapb_ctx::V2Layer& v = c->v2[3];
-        gemm(mX, kD, v.g1, v.n_g1, F2_OUT_F32, v.nln_g1, v.s_g1, v.c_g1, 0, nullptr, nullptr, 512, 0);
+        gemm(mX, kD, v.g1, v.n_g1, F2_OUT_F32, v.nln_g1, v.s_g1, v.c_g1, 0, nullptr, nullptr, nullptr, 512, 0);
         ops.back().f.out_f = c->QKV;
         ops.back().f.out_f2 = c->KVc;
         ops.back().f.side = F2_SIDE_GATHER_LAST;
