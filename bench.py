@@ -252,6 +252,9 @@ def run_ours(args):
     eng = VapEngine(wts, FRAME_HZ, T, max_streams=B, head=args.head, device=local)
     eng.set_option("gemm", args.gemm)
     eng.set_option("graph", 1)
+    for kv in args.opt:                      # experiments only: engine options on top of the defaults
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
 
     n_chunks = T + W + K + 2
     pool = min(n_chunks, 16)                                  # distinct input chunks cycled through
@@ -519,6 +522,7 @@ def main():
     ap.add_argument("--gemm", type=int, default=1, help="1 = tcgen05 bf16x3 GEMMs (product path), 0 = fp32 CUDA-core GEMMs")
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (experiments; the defaults are the product path)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     custom = any(getattr(args, k) is not None and getattr(args, k) != cfg[k] for k in ("batch_per_gpu", "ctx_frames", "head"))

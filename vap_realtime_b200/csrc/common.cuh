@@ -229,6 +229,9 @@ struct TailArgs {
 };
 void launch_tail(const TailArgs& a, cudaStream_t st);
 
+// pulls `n` buffers (device arrays of pointers / byte counts) into L2, one prefetch per 128-byte line
+void launch_l2_prefetch(const void* const* ptrs, const unsigned long long* bytes, int n, unsigned long long total_lines, cudaStream_t st);
+
 // ---- bulk offline scoring (vap_offline.py:51-73 over a whole file) ----
 // chunk rows, channel-major: dst[(ch * n_chunks + b)][0..S) = audio[ch][shift * (first + b) .. + S)
 void launch_make_chunks(const float* audio, long long n_samples, int shift, int S, long long first, int n_chunks, float* dst, cudaStream_t st);

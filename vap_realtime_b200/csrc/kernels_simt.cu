@@ -1320,9 +1320,16 @@ __device__ __forceinline__ void tail_dsm_store(float* local, uint32_t rank, floa
 // into every CTA's `out` through distributed shared memory, one cluster barrier publishes it.  A single SM pulls only
 // ~40 B/clk out of L2: splitting the columns over four SMs is what makes the weight stream short.
 __device__ __forceinline__ void tail_lin256(const float* __restrict__ WT, int ldw, int K, const float* in, int ldin, float* part, float* out,
-                                            int tid, uint32_t crank) {
+                                            int tid, uint32_t crank, const float* __restrict__ nextWT = nullptr, int next_ldw = 0, int nextK = 0) {
     const int nq = tid & 15, kq = tid >> 4;
     const int kper = K >> 4, k0 = kq * kper;              // 16 (K = 256) or 48 (K = 768)
+    if (nextWT) {
+        // the weights of the NEXT layer were last touched a step ago and have usually been evicted from L2 by the
+        // activation planes of the step: start pulling this thread's rows of them into L2 now
+        const int nkper = nextK >> 4;
+        const float* np = nextWT + (size_t)(kq * nkper) * next_ldw + 64 * crank + 4 * nq;
+        for (int k = 0; k < nkper; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + (size_t)k * next_ldw));
+    }
     float acc[kTailRows][4];
 #pragma unroll
     for (int r = 0; r < kTailRows; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
@@ -1503,36 +1510,40 @@ __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(256) k_ta
         const int rr = i >> 8, bs = b0 + (rr >> 1);
         x[i] = bs < a.B ? a.Xl[(size_t)(2 * bs + (rr & 1)) * kD + (i & 255)] : 0.f;
     }
+    {   // first layer's weight rows of this thread -> L2 (see tail_lin256)
+        const float* np = a.WqT + (size_t)((tid >> 4) * 16) * kD + 64 * crank + 4 * (tid & 15);
+        for (int k = 0; k < 16; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + (size_t)k * kD));
+    }
     __syncthreads();
     tail_cluster_sync();                     // every CTA of the cluster is running before the first remote store
     // ---- self attention of the newest frame (modules.py:268-272)
     tail_ln_rows(x, z, a.ln_sa_w, a.ln_sa_b, warp, lane, false);
-    tail_lin256(a.WqT, kD, kD, z, kD, part, bA, tid, crank);
+    tail_lin256(a.WqT, kD, kD, z, kD, part, bA, tid, crank, a.WprojT, kD, kD);
     tail_attention(a.KVs, 0, a.slopes_s, bA, bB, z, b0, a.B, T, a.tvalid, warp, lane, crank);
-    tail_lin256(a.WprojT, kD, kD, bB, kD, part, bC, tid, crank);
+    tail_lin256(a.WprojT, kD, kD, bB, kD, part, bC, tid, crank, a.WqcT, kD, kD);
     for (int i = tid; i < kTailRows * kD; i += 256) x[i] += bC[i];
     __syncthreads();
     // ---- cross attention: query from LN_src(x), keys / values of the sibling channel (modules.py:276-283)
     tail_ln_rows(x, z, a.ln_src_w, a.ln_src_b, warp, lane, false);
-    tail_lin256(a.WqcT, kD, kD, z, kD, part, bA, tid, crank);
+    tail_lin256(a.WqcT, kD, kD, z, kD, part, bA, tid, crank, a.WprojcT, kD, kD);
     tail_attention(a.KVc, 1, a.slopes_c, bA, bB, z, b0, a.B, T, a.tvalid, warp, lane, crank);
-    tail_lin256(a.WprojcT, kD, kD, bB, kD, part, bD, tid, crank);
+    tail_lin256(a.WprojcT, kD, kD, bB, kD, part, bD, tid, crank, a.W1T, kFF, kD);
     for (int i = tid; i < kTailRows * kD; i += 256) x[i] += bD[i];
     __syncthreads();
     // ---- feed forward (modules.py:9-21, 285)
     tail_ln_rows(x, z, a.ln_ff_w, a.ln_ff_b, warp, lane, false);
     for (int j = 0; j < 3; ++j) {
         float* o = (j == 1) ? bC : bA;
-        tail_lin256(a.W1T + 256 * j, kFF, kD, z, kD, part, o, tid, crank);
+        tail_lin256(a.W1T + 256 * j, kFF, kD, z, kD, part, o, tid, crank, j < 2 ? a.W1T + 256 * (j + 1) : a.W2T, j < 2 ? kFF : kD, j < 2 ? kD : kFF);
         for (int i = tid; i < kTailRows * kD; i += 256) hd[(i >> 8) * kFF + 256 * j + (i & 255)] = gelu_erf(o[i]);
     }
     __syncthreads();
-    tail_lin256(a.W2T, kD, kFF, hd, kFF, part, bC, tid, crank);
+    tail_lin256(a.W2T, kD, kFF, hd, kFF, part, bC, tid, crank, a.WaT, kD, kD);
     for (int i = tid; i < kTailRows * kD; i += 256) x[i] += bC[i];
     __syncthreads();
     // ---- Combinator: GELU(LN(h0_a x_ch0)) + GELU(LN(h0_b x_ch1)), one shared LayerNorm (modules.py:461-464)
-    tail_lin256(a.WaT, kD, kD, x, kD, part, bA, tid, crank);          // every row through h0_a: the channel-0 rows are used
-    tail_lin256(a.WbT, kD, kD, x, kD, part, bD, tid, crank);          // every row through h0_b: the channel-1 rows are used
+    tail_lin256(a.WaT, kD, kD, x, kD, part, bA, tid, crank, a.WbT, kD, kD);          // every row through h0_a: the channel-0 rows are used
+    tail_lin256(a.WbT, kD, kD, x, kD, part, bD, tid, crank, a.head_kind == 0 ? a.WhT : nullptr, kD, kD);          // every row through h0_b: the channel-1 rows are used
     for (int i = tid; i < kTailRows * kD; i += 256) {
         const int rr = i >> 8;
         z[i] = (rr & 1) ? bD[i] : bA[i];
@@ -1645,6 +1656,26 @@ __global__ void __launch_bounds__(64) k_gather_windows(const float* __restrict__
 }
 void launch_gather_windows(const float* E, long long n_frames, long long first, int B, int T, float* X, int* tvalid, int* ids_out, cudaStream_t st) {
     launch_k(k_gather_windows, dim3(2 * B), dim3(64), 0, st, E, n_frames, first, B, T, X, tvalid, ids_out);
+}
+
+// -----------------------------------------------------------------------------------------
+// L2 warm-up of the transformer / tail weights, launched on a side branch of the step graph next to the encoder: a
+// real-time stream leaves 50 ms between steps, so the weights of the later kernels start a step in HBM, and the per-stream
+// cluster kernel otherwise pays the DRAM latency of every weight tile once per launch on its critical path.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_l2_prefetch(const void* const* __restrict__ ptrs, const unsigned long long* __restrict__ bytes, int n) {
+    unsigned long long line = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long nl = (bytes[i] + 127ull) >> 7;
+        if (line < nl) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ptrs[i]) + (line << 7)));
+            return;
+        }
+        line -= nl;
+    }
+}
+void launch_l2_prefetch(const void* const* ptrs, const unsigned long long* bytes, int n, unsigned long long total_lines, cudaStream_t st) {
+    launch_k(k_l2_prefetch, dim3((unsigned)((total_lines + 255) / 256)), dim3(256), 0, st, ptrs, bytes, n);
 }
 
 }  // namespace vapb

@@ -98,7 +98,13 @@ struct vapb_ctx {
     float *t_WqT = nullptr, *t_WprojT = nullptr, *t_WqcT = nullptr, *t_WprojcT = nullptr, *t_W1T = nullptr, *t_W2T = nullptr,
           *t_WaT = nullptr, *t_WbT = nullptr, *t_WhT = nullptr;
     int opt_tail = 1;                // 1 = k_tail (one kernel), 0 = the nine per-op kernels
-    int opt_conv12_ks = 0;           // experiment: split-K of conv1 (low nibble) and conv2 (high nibble); 0 = none
+    int opt_conv12_ks = 0;
+    // L2 warm-up of the weights behind the encoder (side branch of the step graph)
+    const void** pf_ptrs = nullptr;
+    unsigned long long* pf_bytes = nullptr;
+    int pf_n = 0;
+    unsigned long long pf_lines = 0;
+    int opt_prefetch = 0;            // measured: 0.586 vs 0.579 ms per step in the flushed bench: no gain, off           // experiment: split-K of conv1 (low nibble) and conv2 (high nibble); 0 = none
     float *va_w = nullptr, *va_b = nullptr;
 
     // per-stream state
@@ -881,7 +887,17 @@ void enqueue_step(Step& s) {
     vapb::g_attn_rk = c->opt_attn_rk != 0;
     const int B = s.B, NC = 2 * B, T = c->T;
     cudaStream_t st = s.st;
+    // side branch: pull the transformer / tail weights into L2 while the encoder runs
+    const bool prefetch = c->opt_prefetch && c->opt_gemm == 1 && c->pf_n > 0 && s.prof == nullptr;
+    if (prefetch) {
+        cudaEventRecord(c->ev_fork, st);
+        cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0);
+        launch_l2_prefetch(c->pf_ptrs, c->pf_bytes, c->pf_n, c->pf_lines, c->side_stream);
+        cudaEventRecord(c->ev_join, c->side_stream);
+        s.n += 1;
+    }
     encoder_convs(s, NC);
+    if (prefetch) cudaStreamWaitEvent(st, c->ev_join, 0);      // joined early: the warm-up itself takes a few microseconds
     {
         const RowMap g4 = plain_map(4 * kD);
         if (c->opt_lstm_fused) {
@@ -1208,6 +1224,37 @@ int vapb_create(const void* weights_blob, size_t nbytes, int frame_hz, int ctx_f
     c->h_qkv.assign(MS, 0);
     if (build_fused_ops(c) != 0) FAIL_CREATE(VAPB_ECUDA, "%s", c->err.c_str());
     if (build_fused2(c) != 0) FAIL_CREATE(VAPB_ECUDA, "%s", c->err.c_str());
+    {   // weights the kernels behind the encoder read: bf16 planes of the transformer GEMMs, k-major tail weights
+        std::vector<const void*> ptrs;
+        std::vector<unsigned long long> bytes;
+        auto add_tc = [&](const TcWeight& w) {
+            if (!w.hi) return;
+            ptrs.push_back(w.hi); bytes.push_back((unsigned long long)w.N * w.K * 2);
+            ptrs.push_back(w.lo); bytes.push_back((unsigned long long)w.N * w.K * 2);
+        };
+        auto add_f = [&](const float* p, size_t n) { if (p) { ptrs.push_back(p); bytes.push_back((unsigned long long)n * 4); } };
+        const bool v2 = c->f2ops != nullptr;
+        for (int l = 0; l < 4; ++l) {
+            const LayerWeights& lw = c->layers[l];
+            if (v2) { add_tc(c->v2[l].g1); add_tc(c->v2[l].qc); add_tc(c->v2[l].w1); }
+            else { add_tc(l < 3 ? lw.sa.tc_qkv : lw.sa.tc_kv); add_tc(lw.tc_kv_c); if (l < 3) { add_tc(lw.tc_q_c); add_tc(lw.tc_w1); } }
+            if (l < 3) { add_tc(lw.sa.tc_proj); add_tc(lw.tc_proj_c); add_tc(lw.tc_w2); }
+        }
+        add_f(c->t_WqT, 65536); add_f(c->t_WprojT, 65536); add_f(c->t_WqcT, 65536); add_f(c->t_WprojcT, 65536);
+        add_f(c->t_W1T, 196608); add_f(c->t_W2T, 196608); add_f(c->t_WaT, 65536); add_f(c->t_WbT, 65536);
+        if (head_kind == VAPB_HEAD_VAP) add_f(c->t_WhT, 65536);
+        c->pf_n = (int)ptrs.size();
+        for (unsigned long long b : bytes) c->pf_lines += (b + 127) >> 7;
+        void* d = nullptr;
+        if (cudaMalloc(&d, ptrs.size() * sizeof(void*)) != cudaSuccess) FAIL_CREATE(VAPB_ENOMEM, "cudaMalloc failed");
+        c->allocs.push_back(d);
+        cudaMemcpy(d, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice);
+        c->pf_ptrs = static_cast<const void**>(d);
+        if (cudaMalloc(&d, bytes.size() * sizeof(unsigned long long)) != cudaSuccess) FAIL_CREATE(VAPB_ENOMEM, "cudaMalloc failed");
+        c->allocs.push_back(d);
+        cudaMemcpy(d, bytes.data(), bytes.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+        c->pf_bytes = static_cast<unsigned long long*>(d);
+    }
 
     // taps (allocated lazily when keep_taps is switched on)
     if (cudaDeviceSynchronize() != cudaSuccess) FAIL_CREATE(VAPB_ECUDA, "device error during create: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1481,7 +1528,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         }
         h->opt_gemm = value;
     } else if (k == "timing") h->opt_timing = value ? 1 : 0;
-    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v" || k == "tail" || k == "lstm_x_tc" || k == "qkv_cache" || k == "conv12_ks") {
+    else if (k == "lstm_fused" || k == "tile_n" || k == "fuse_ln" || k == "k256" || k == "pdl" || k == "prune" || k == "attn_rk" || k == "fork" || k == "splitk" || k == "conv4p" || k == "cluster2" || k == "fused" || k == "fused_dbg" || k == "fused_v" || k == "tail" || k == "lstm_x_tc" || k == "qkv_cache" || k == "conv12_ks" || k == "prefetch") {
         if (k == "tile_n" && value != 0 && value != 64 && value != 128 && value != 256) return fail(h, VAPB_EINVAL, "tile_n must be 0, 64, 128 or 256");
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -1504,6 +1551,7 @@ int vapb_set_option(vapb_handle h, const char* key, int value) {
         else if (k == "lstm_x_tc") h->opt_lstm_x_tc = value ? 1 : 0;
         else if (k == "qkv_cache") h->opt_qkv_cache = value ? 1 : 0;
         else if (k == "conv12_ks") h->opt_conv12_ks = value & 0xff;
+        else if (k == "prefetch") h->opt_prefetch = value ? 1 : 0;
         else { h->opt_tile_n = value; h->tcws.force_bn = value; }
     } else if (k == "keep_taps") {
         h->opt_keep_taps = value ? 1 : 0;
@@ -1544,6 +1592,7 @@ int vapb_get_option(vapb_handle h, const char* key, int* value) {
     else if (k == "lstm_x_tc") *value = h->opt_lstm_x_tc;
     else if (k == "qkv_cache") *value = h->opt_qkv_cache;
     else if (k == "conv12_ks") *value = h->opt_conv12_ks;
+    else if (k == "prefetch") *value = h->opt_prefetch;
     else if (k == "fused_v") *value = (h->opt_fused_v == 2 && h->f2ops) ? 2 : 1;
     else if (k == "keep_taps") *value = h->opt_keep_taps;
     else return fail(h, VAPB_EINVAL, "unknown option %s", key);
