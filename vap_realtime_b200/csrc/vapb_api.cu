@@ -880,6 +880,7 @@ void encoder_convs(Step& s, int NC) {
 
 void transformer_batched(Step& s, bool prune, bool qkv_cached);
 void tail_or_head(Step& s, bool prune, int* count);
+bool step_uses_stream(const vapb_ctx* c, int B);
 
 void enqueue_step(Step& s) {
     vapb_ctx* c = s.c;
@@ -916,12 +917,10 @@ void enqueue_step(Step& s) {
             launch_scatter_state(c->hS, c->cS, c->ids_dev, c->hW, c->cW, B, st); mark(s, "lstm_state");
         }
     }
-    // one cluster per stream: a win while all clusters are co-resident (2B <= SM count); bigger batches are served
-    // better by the batched per-op kernels, whose GEMM tiles are full (measured B = 128 / 256: r01_n_experiments.md)
+    // per-stream cluster kernel or batched per-op kernels: see step_uses_stream
     const bool prune = c->opt_prune && !c->opt_keep_taps;      // taps want every position of every layer
     const bool v2 = c->opt_fused_v == 2 && c->f2ops;
-    const int stream_ctas = v2 ? 4 * ((B + 1) / 2) : 2 * B;       // v2: clusters of four CTAs = two streams
-    const bool use_stream = c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (stream_ctas <= c->sm_count || c->opt_fused == 2);
+    const bool use_stream = step_uses_stream(c, B);
     // ---- downsample conv over exactly n_lstm frames + LayerNorm + GELU -> ring
     {
         const int Kd = c->n_lstm * kD;
@@ -953,12 +952,21 @@ void enqueue_step(Step& s) {
     tail_or_head(s, prune, c->count);
 }
 
-// same decision as enqueue_step: does a batch of B run the per-stream cluster kernel (which recomputes layer 0)?
+// Does a batch of B run the per-stream cluster kernel (which recomputes layer 0) or the batched per-op kernels?
+// One wave of clusters holds `cap` streams (74 on a 148-SM part, either generation).  Up to one wave the stream kernel
+// always wins.  Beyond it the launch runs in waves whose last one costs as much as a full one, so it only pays when the
+// waves are well filled: measured (tools/big_batch_paths.py, profiles/r02_q_*) T = 50: B = 128 / 192 +3 % / +6 %,
+// B = 96 / 256 / 1024 -4 % / -5 % / -13 %; T = 100 (one channel per CTA, first generation): +12 ... +18 % at B = 128 / 256 / 1024.
 bool step_uses_stream(const vapb_ctx* c, int B) {
     const bool prune = c->opt_prune && !c->opt_keep_taps;
+    if (!(c->opt_gemm == 1 && c->opt_fused && prune && c->fops)) return false;
+    if (c->opt_fused == 2) return true;
     const bool v2 = c->opt_fused_v == 2 && c->f2ops;
-    const int stream_ctas = v2 ? 4 * ((B + 1) / 2) : 2 * B;
-    return c->opt_gemm == 1 && c->opt_fused && prune && c->fops && (stream_ctas <= c->sm_count || c->opt_fused == 2);
+    const int cap = v2 ? 2 * (c->sm_count / 4) : c->sm_count / 2;
+    if (B <= cap) return true;
+    const int waves = (B + cap - 1) / cap;
+    const bool filled = (long long)B * 100 >= 85ll * waves * cap;
+    return c->T > 64 ? filled : (filled && waves <= 3);
 }
 
 // Layer-0 Q/K/V cache bookkeeping in front of a step: a stream whose cached rows do not cover all its frames (it was
