@@ -161,22 +161,36 @@ __device__ __forceinline__ void stg_put_co(uint32_t stg, int lane, int i, uint4 
 // staging tile (32 rows x 128 bytes, exactly the SWIZZLE_128B box layout) -> global through ONE TMA store issued by lane 0.
 // The LSU never sees these bytes: thread-per-row st.global made the first cut of this kernel slower than its predecessor,
 // coalesced st.global through the tile still cost ~150 k cycles per launch (timing-only builds without the stores).
-// Returns when the tile may be rewritten (the TMA engine has read it); completion of the writes is awaited once per op.
-template <bool PLANE>
+// WAIT: returns when the tile may be rewritten (the TMA engine has read it); otherwise the caller runs stg_wait_read()
+// before it touches the tile again, with independent work in between (-16 k cycles per launch against waiting in place).
+// Completion of the writes is awaited once per op.  Measured and not kept: sending the last subtile's second plane through
+// tiles borrowed from the idle A ring so that no read-wait is left at the end of an op (+12 k cycles: the kernel is
+// sensitive to code size), see profiles/r02_r_*.
+#ifdef VAPB_F2_EAGERWAIT
+#define F2_EAGER true
+#else
+#define F2_EAGER false
+#endif
+template <bool PLANE, bool WAIT = true>
 __device__ __forceinline__ void stg_tma_store_2d(uint32_t stg, int lane, const CUtensorMap* map, int c0, int c1) {
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
         if (PLANE) { F2_STORE_P(tma_store_2d(map, c0, c1, stg);) } else { F2_STORE(tma_store_2d(map, c0, c1, stg);) }
         tma_store_commit();
-        tma_store_wait_read();
+        if (WAIT || F2_EAGER) tma_store_wait_read();
     }
     __syncwarp();
 }
+__device__ __forceinline__ void stg_wait_read(int lane) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+}
 // a thread's 64 packed bf16 pairs (32 words = the 128 bytes of one plane row) -> plane rows [row0, row0 + 32), columns [col, col + 64)
+template <bool WAIT>
 __device__ __forceinline__ void store_plane_rows(uint32_t stg, int lane, const uint32_t* w, const CUtensorMap* map, int col, int row0) {
     stg_put_row(stg, lane, w);
-    stg_tma_store_2d<true>(stg, lane, map, col, row0);
+    stg_tma_store_2d<true, WAIT>(stg, lane, map, col, row0);
 }
 // end of an op: every store this warp issued is complete before the op barrier publishes the results
 __device__ __forceinline__ void stores_done(int lane) {
@@ -279,8 +293,9 @@ __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, con
 #pragma unroll
             for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[16 * blk + e], L[16 * blk + e]);
         }
-        store_plane_rows(stg, c.lane, H, &gop->m[4], col0, grow0);
-        store_plane_rows(stg, c.lane, L, &gop->m[5], col0, grow0);
+        stg_wait_read(c.lane);                                  // the previous subtile's lo plane: read while this one was computed
+        store_plane_rows<true>(stg, c.lane, H, &gop->m[4], col0, grow0);
+        store_plane_rows<false>(stg, c.lane, L, &gop->m[5], col0, grow0);
     }
     stores_done(c.lane);
     if (fine) fine[3] = clock64();
@@ -311,6 +326,7 @@ __device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Op* gop, const F2
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
             const int col = col0 + 32 * blk;
+            stg_wait_read(c.lane);                              // the store issued before this point has left the tile
 #pragma unroll
             for (int i = 0; i < 8; ++i) stg_put_co(stg, c.lane, i, rc[i]);
             __syncwarp();
@@ -335,12 +351,13 @@ __device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Op* gop, const F2
                 for (int e = 0; e < 32; ++e) vb[e] = __float_as_uint(v[e]);
                 stg_put_row(stg, c.lane, vb);
             }
-            stg_tma_store_2d<false>(stg, c.lane, &gop->m[6], col, grow0);          // fp32 residual stream
+            stg_tma_store_2d<false, false>(stg, c.lane, &gop->m[6], col, grow0);   // fp32 residual stream (read while the planes are split)
 #pragma unroll
             for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[16 * blk + e], L[16 * blk + e]);
         }
-        store_plane_rows(stg, c.lane, H, &gop->m[4], col0, grow0);
-        store_plane_rows(stg, c.lane, L, &gop->m[5], col0, grow0);
+        stg_wait_read(c.lane);
+        store_plane_rows<true>(stg, c.lane, H, &gop->m[4], col0, grow0);
+        store_plane_rows<false>(stg, c.lane, L, &gop->m[5], col0, grow0);
     }
     stores_done(c.lane);
     if (fine) fine[3] = clock64();
@@ -372,6 +389,7 @@ __device__ __noinline__ void epilogue_f32(const Ctx2& c, const F2Op* gop, const 
             uint32_t vb[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) vb[e] = __float_as_uint(v[e]);
+            stg_wait_read(c.lane);                              // the previous block's store: read during this block's load + correction
             stg_put_row(stg, c.lane, vb);
             // rows 32q .. 32q + 31 of the tile = positions 32 (q & 1) .. + 31 of sequence q >> 1; positions >= T are clipped by the map
             if (!c.ghost) {
@@ -380,7 +398,7 @@ __device__ __noinline__ void epilogue_f32(const Ctx2& c, const F2Op* gop, const 
                 if (c.lane == 0) {
                     F2_STORE(tma_store_3d(&gop->m[col < 512 ? 4 : 5], col & 511, 32 * (q & 1), 2 * c.b + (q >> 1), stg);)
                     tma_store_commit();
-                    tma_store_wait_read();
+                    if (F2_EAGER) tma_store_wait_read();
                 }
             }
             __syncwarp();
@@ -400,7 +418,7 @@ __device__ __forceinline__ void gemm_epilogue(const Ctx2& c, const F2Fields& op,
 
 // ============================== GEMM: tile schedule ==============================
 // Subtiles go in groups: a PAIR of subtiles (two W tiles per k-block, two 128-column accumulators issued interleaved)
-// or a SINGLE subtile (one W tile per k-block, issued as two N = 64 halves).  The A tiles stream once per group.
+// or a SINGLE subtile (one W tile per k-block, one chain of N = 128 MMAs).  The A tiles stream once per group.
 __device__ __forceinline__ int gemm_groups(const F2Fields& op) { return ((op.N >> 8) + 1) >> 1; }
 __device__ __forceinline__ int gemm_a_tiles(const F2Fields& op) { return (op.K >> 6) * gemm_groups(op); }     // even (K/64 is 4 or 12)
 __device__ __forceinline__ int gemm_w_tiles(const F2Fields& op) { return (op.N >> 8) * (op.K >> 6); }
@@ -449,7 +467,13 @@ __device__ __forceinline__ void gemm_tma_a(const Ctx2& c, const F2Op* gop, const
 // ============================== GEMM: MMA side (one elected thread) ==============================
 template <bool PAIR>
 __device__ __forceinline__ void mma_group(const Ctx2& c, int nkb, bool first_group, int& ai, int& w, int slot0, int slot1) {
+#ifdef VAPB_F2_SINGLE64
+    constexpr bool kTwo = true;                           // experiment: single groups as two interleaved N = 64 halves
     constexpr uint32_t idesc = PAIR ? make_idesc(128) : make_idesc(64);
+#else
+    constexpr bool kTwo = PAIR;                           // a single group is ONE chain of N = 128 MMAs: the two-halves form read every A tile twice
+    constexpr uint32_t idesc = make_idesc(128);
+#endif
     const uint32_t acc0 = c.tmem_base + (uint32_t)(slot0 * 128);
     const uint32_t acc1 = PAIR ? c.tmem_base + (uint32_t)(slot1 * 128) : acc0 + 64u;
     for (int kb = 0; kb < nkb; ++kb, ++ai) {
@@ -475,11 +499,11 @@ __device__ __forceinline__ void mma_group(const Ctx2& c, int nkb, bool first_gro
             const uint32_t first = (kb | k) ? 1u : 0u;
             // small terms first: lo * hi, hi * lo, then hi * hi; the two accumulators alternate
             umma_bf16(acc0, make_desc(ab + kPlane + koff), make_desc(wb0 + koff), idesc, first);
-            umma_bf16(acc1, make_desc(ab + kPlane + koff), make_desc(wb1 + koff), idesc, first);
+            if (kTwo) umma_bf16(acc1, make_desc(ab + kPlane + koff), make_desc(wb1 + koff), idesc, first);
             umma_bf16(acc0, make_desc(ab + koff), make_desc(wb0 + kPlane + koff), idesc, 1u);
-            umma_bf16(acc1, make_desc(ab + koff), make_desc(wb1 + kPlane + koff), idesc, 1u);
+            if (kTwo) umma_bf16(acc1, make_desc(ab + koff), make_desc(wb1 + kPlane + koff), idesc, 1u);
             umma_bf16(acc0, make_desc(ab + koff), make_desc(wb0 + koff), idesc, 1u);
-            umma_bf16(acc1, make_desc(ab + koff), make_desc(wb1 + koff), idesc, 1u);
+            if (kTwo) umma_bf16(acc1, make_desc(ab + koff), make_desc(wb1 + koff), idesc, 1u);
         }
         umma_commit_mc(c.w_empty(ws0), c.mask_w);
         if (PAIR) umma_commit_mc(c.w_empty(ws1), c.mask_w);
@@ -668,8 +692,8 @@ __device__ __noinline__ void attn_workers(const Ctx2& c, const F2Op* gop, const 
     }
     tc_fence_before();
     const int grow0 = c.b * 128 + 32 * q;
-    store_plane_rows(c.stg(), c.lane, H, &gop->m[4], head * 64, grow0);
-    store_plane_rows(c.stg(), c.lane, L, &gop->m[5], head * 64, grow0);
+    store_plane_rows<true>(c.stg(), c.lane, H, &gop->m[4], head * 64, grow0);
+    store_plane_rows<false>(c.stg(), c.lane, L, &gop->m[5], head * 64, grow0);
     stores_done(c.lane);
 }
 
