@@ -368,12 +368,12 @@ def run_ours(args):
             for i in range(n):
                 k = one_step(host=True)
                 if k >= 1 and rank == 0:
-                    out_h.copy_(pipe.results(k - 1), non_blocking=True)
-                    torch.cuda.current_stream(dev).synchronize()
+                    pipe.results_host(k - 1, out=out_h)          # D2H on its own stream: does not wait for step k
             k_last = pipe.n - 1
-            res = pipe.results(k_last)
             if rank == 0:
-                out_h.copy_(res, non_blocking=True)
+                pipe.results_host(k_last, out=out_h)
+            else:
+                pipe.results(k_last)
             torch.cuda.synchronize()
 
         e2e_loop(3)
@@ -467,6 +467,8 @@ def run_ours(args):
             if dom["kind"] == "stream":
                 fl = B * stream_kernel_gflop_per_frame(T) * 1e9
                 gen = eng.get_option("fused_v")
+                if not (B == 64 and T == 50 and gen == 2 and launches_per_step == 14):
+                    traffic, tsrc = None, "the ncu capture is of config 2 (B = 64, T = 50, stream kernel v2, one wave) only"
                 name = (("k_stream_tf2 (second generation: clusters of four CTAs = two streams, TMA-fed multicast operands, LayerNorm folded "
                          "into the epilogue)" if gen == 2 else "k_stream_tf (first generation: a cluster of two CTAs per stream, A operand in tensor memory)")
                         + ": per-stream persistent transformer kernel (ring gather, ar_channel layer, vad, cross layers 0-1, K/V of the "

@@ -60,7 +60,9 @@ def _worker(rank, world, port, n_streams, n_steps, q, pipelined=False):
             k = pipe.push(chunk if rank == 0 else None)
             if k >= 1:
                 outs.append(pipe.results(k - 1).clone())
-        outs.append(pipe.results(n_steps - 1).clone())
+        last = pipe.results(n_steps - 1).clone()
+        assert torch.equal(pipe.results_host(n_steps - 1), last)            # the host-copy form returns the same rows
+        outs.append(last)
         with pytest.raises(ValueError):
             pipe.results(0)
         n_steps = 0

@@ -50,7 +50,7 @@ piped = []
 for n in range(n_steps):
     k = pipe.push(host[n] if rank == 0 else None)
     if k >= 1:
-        piped.append(pipe.results(k - 1).cpu().clone())
+        piped.append(pipe.results_host(k - 1).clone() if n % 2 else pipe.results(k - 1).cpu().clone())      # both read forms
 piped.append(pipe.results(n_steps - 1).cpu().clone())
 torch.cuda.synchronize()
 if rank == 0:
