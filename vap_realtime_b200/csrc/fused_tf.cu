@@ -895,7 +895,10 @@ __global__ void __launch_bounds__(kThreadsF, 1) k_stream_tf(const FusedParams p)
         else if (c.warp == kWorkers + 1) mma_loop(c, p);
         else {
             // two spare warps complete the third warpgroup; the first one runs the small side tasks next to the op that
-            // allows it (they only read X, which that op does not modify), so they cost no cluster barrier of their own
+            // allows it (they only read X, which that op does not modify), so they cost no cluster barrier of their own;
+            // the second one fetches every op's tensor maps up front (the op program is cold when a step starts)
+            if (c.warp == kWorkers + 3)
+                for (int i = c.lane; i < p.n_ops * 2; i += 32) prefetch_tmap(i & 1 ? &p.ops[i >> 1].map_lo : &p.ops[i >> 1].map_hi);
             for (int oi = 0; oi < p.n_ops; ++oi) {
                 const int side = c.warp == kWorkers + 2 ? __ldg(&p.ops[oi].f.side) : 0;
                 if (side == FSIDE_VAD) {

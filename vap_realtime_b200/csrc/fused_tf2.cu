@@ -731,28 +731,36 @@ __device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int
     const size_t grow0 = (size_t)c.b * 128 + 64 * ch;
     const bool ds = p.ds_part != nullptr && !c.ghost;
     const int jnew = ds ? c.t - 1 : -1;
-    for (int j0 = c.warp; j0 < 64; j0 += 2 * kWorkers2) {          // two rows per pass: both loads in flight
-        float v[2][8];
+    // the warp's 8 rows (warp + 8u): every load is in flight before the first row is emitted -- the ring comes from HBM
+    // (nothing has touched it since the previous step), and a row-at-a-time loop paid that latency four times over
+    float4 va[8], vb[8];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int j = j0 + u * kWorkers2;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
-            if (j < c.t && j != jnew) {
-                const int slot = (cnt - c.t + j) % p.T;
-                const float4 a = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane + 4));
-                v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int j = j0 + u * kWorkers2;
-            if (j != jnew) emit_row(p, grow0 + j, c.lane, v[u]);
+    for (int u = 0; u < 8; ++u) {
+        const int j = c.warp + u * kWorkers2;
+        va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[u] = va[u];
+        if (j < c.t && j != jnew) {
+            const int slot = (cnt - c.t + j) % p.T;
+            va[u] = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane));
+            vb[u] = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane + 4));
         }
     }
-    if (ds && c.warp == kWorkers2 - 1) {
-        // newest embedding: split-K sum of the downsample GEMM, LayerNorm, exact GELU (encoder_components.py:496-511)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int j = c.warp + u * kWorkers2;
+        const float v8[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+        if (j != jnew) emit_row(p, grow0 + j, c.lane, v8);
+    }
+    if (c.r == 0 && c.tid == 0 && !c.ghost) p.tvalid[c.b] = c.t;
+}
+
+// The newest embedding of channel r (one warp, the side-task warp, while the workers gather the older rows): split-K sum of
+// the downsample GEMM, LayerNorm, exact GELU (encoder_components.py:496-511) -> ring slot, e_out, X row t - 1.
+__device__ __noinline__ void ds_tail_op(const Ctx2& c, const Fused2Params& p, int id, int cnt) {
+    const int ch = c.r;
+    const size_t grow0 = (size_t)c.b * 128 + 64 * ch;
+    const bool ds = p.ds_part != nullptr && !c.ghost;
+    if (ds) {
         const int n = 2 * c.b + ch;
         const float* pr = p.ds_part + (size_t)n * kD + 8 * c.lane;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
@@ -799,7 +807,6 @@ __device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int
             }
         emit_row(p, grow0 + (c.t - 1), c.lane, v8);
     }
-    if (c.r == 0 && c.tid == 0 && !c.ghost) p.tvalid[c.b] = c.t;
 }
 
 // ============================== op loop ==============================
@@ -855,6 +862,14 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
 
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && c.tid == 0;
 
+#ifndef VAPB_F2_NO_TMAP_PREFETCH
+    // the op program (7 tensor maps per op) is as cold as everything else when a step starts: fetch all of it now, not at
+    // the first TMA instruction of each op (-7 us per step).  The MMA and A-producer warps do it: they idle through op 0
+    // (the gather), and a prefetch.tensormap holds its warp for a while (issued by the side warp in front of the
+    // newest-frame tail they made the gather 10 k cycles longer).
+    if (c.warp == kWorkers2 + 1 || c.warp == kWorkers2 + 2)
+        for (int i = (c.warp - kWorkers2 - 1) * 32 + c.lane; i < (p.n_ops - 1) * 7; i += 64) prefetch_tmap(&p.ops[1 + i / 7].m[i % 7]);      // op 0 has no maps
+#endif
     if (c.warp == kWorkers2) {
         // ---------------- W producer: free-running, reads the op list from global memory ----------------
         int wt = 0;
@@ -920,7 +935,9 @@ __global__ void __launch_bounds__(kThreads2, 1) k_stream_tf2(const Fused2Params 
                 __syncwarp();
             } else {
                 const int side = c.ghost ? F2_SIDE_NONE : __shfl_sync(0xffffffffu, op.side, 0);
-                if (side == F2_SIDE_VAD) {
+                if (kind == F2_GATHER) {
+                    ds_tail_op(c, p, id, cnt);
+                } else if (side == F2_SIDE_VAD) {
                     // vad = sigmoid(va_classifier(x[t-1])) on the ar_channel output (vap_main.py:292-293, 313-314)
                     const float* xr = p.Xf + ((size_t)c.b * 128 + 64 * c.r + (c.t - 1)) * kD + 8 * c.lane;
                     const float4 x0 = __ldcg(reinterpret_cast<const float4*>(xr)), x1 = __ldcg(reinterpret_cast<const float4*>(xr + 4));
