@@ -151,8 +151,7 @@ struct vapb_ctx {
         TcWeight g1, qc, w1;
     } v2[4];
     float *X2f = nullptr, *St2 = nullptr;
-    __nv_bfloat16 *X2h = nullptr, *X2l = nullptr, *G1h = nullptr, *G1l = nullptr, *O2h = nullptr, *O2l = nullptr, *Qc2h = nullptr,
-                  *Qc2l = nullptr, *H2h = nullptr, *H2l = nullptr;
+    __nv_bfloat16 *X2h = nullptr, *X2l = nullptr, *G1h = nullptr, *G1l = nullptr;
     F2Op* f2ops = nullptr;
     int n_f2ops = 0;
     int opt_fused_v = 2;             // 2 = second-generation stream kernel where it applies (T <= 64; measured 581 vs 597 us per step at B = 64), 1 = first generation
@@ -533,11 +532,11 @@ FOp fop_gemm(const float* A, int lda, int K, const TcWeight& w, const float* ln_
     o.f.A = A; o.f.lda = lda; o.f.K = K; o.f.ln_w = ln_w; o.f.ln_b = ln_b; o.f.R = R; o.f.C = C; o.f.ldc = ldc; o.f.N = N; o.f.act = act;
     return o;
 }
-FOp fop_attn(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O, const float* slopes, int sibling) {
+FOp fop_attn(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O, int ldo, const float* slopes, int sibling) {
     FOp o;
     memset(&o, 0, sizeof o);
     o.f.kind = FOP_ATTN;
-    o.f.Q = Q; o.f.ldq = ldq; o.f.Kp = K; o.f.ldk = ldk; o.f.V = V; o.f.ldv = ldv; o.f.O = O; o.f.ldo = kD; o.f.slopes = slopes; o.f.sibling = sibling;
+    o.f.Q = Q; o.f.ldq = ldq; o.f.Kp = K; o.f.ldk = ldk; o.f.V = V; o.f.ldv = ldv; o.f.O = O; o.f.ldo = ldo; o.f.slopes = slopes; o.f.sibling = sibling;
     return o;
 }
 FOp fop_misc(int kind) {
@@ -555,15 +554,21 @@ int build_fused_ops(vapb_ctx* c) {
         const size_t first = ops.size();
         if (lw.cross) ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_kv_c, nullptr, nullptr, nullptr, c->KVc, 2 * kD, 2 * kD, 0));
         ops.push_back(fop_gemm(c->X, kD, kD, lw.sa.tc_qkv, lw.ln_sa_w, lw.ln_sa_b, nullptr, c->QKV, 3 * kD, 3 * kD, 0));
-        ops.push_back(fop_attn(c->QKV, 3 * kD, c->QKV + kD, 3 * kD, c->QKV + 2 * kD, 3 * kD, c->O, lw.sa.slopes, 0));
-        ops.push_back(fop_gemm(c->O, kD, kD, lw.sa.tc_proj, nullptr, nullptr, c->X, c->X, kD, kD, 0));
+        // The [rows][768] Q | K | V buffer carries every other intermediate of the layer as well (a smaller footprint keeps the
+        // scratch rows in L2 instead of streaming dead lines to HBM): the attention writes O over the Q columns of the heads
+        // it has loaded, the cross attention's Q projection and O reuse those 256 columns once the self-attention's
+        // projection has consumed them, and the FFN's hidden rows (768 wide, the same pitch) replace Q | K | V altogether.
+        float* const Osc = c->QKV;
+        ops.push_back(fop_attn(c->QKV, 3 * kD, c->QKV + kD, 3 * kD, c->QKV + 2 * kD, 3 * kD, Osc, 3 * kD, lw.sa.slopes, 0));
+        ops.push_back(fop_gemm(Osc, 3 * kD, kD, lw.sa.tc_proj, nullptr, nullptr, c->X, c->X, kD, kD, 0));
         if (lw.cross) {
-            ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_q_c, lw.ln_src_w, lw.ln_src_b, nullptr, c->Qc, kD, kD, 0));
-            ops.push_back(fop_attn(c->Qc, kD, c->KVc, 2 * kD, c->KVc + kD, 2 * kD, c->O, lw.slopes_c, 1));
-            ops.push_back(fop_gemm(c->O, kD, kD, lw.tc_proj_c, nullptr, nullptr, c->X, c->X, kD, kD, 0));
+            ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_q_c, lw.ln_src_w, lw.ln_src_b, nullptr, Osc, 3 * kD, kD, 0));
+            ops.push_back(fop_attn(Osc, 3 * kD, c->KVc, 2 * kD, c->KVc + kD, 2 * kD, Osc, 3 * kD, lw.slopes_c, 1));
+            ops.push_back(fop_gemm(Osc, 3 * kD, kD, lw.tc_proj_c, nullptr, nullptr, c->X, c->X, kD, kD, 0));
         }
-        ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_w1, lw.ln_ff_w, lw.ln_ff_b, nullptr, c->Hd, kFF, kFF, 1));
-        ops.push_back(fop_gemm(c->Hd, kFF, kFF, lw.tc_w2, nullptr, nullptr, c->X, c->X, kD, kD, 0));
+        static_assert(kFF == 3 * kD, "the FFN hidden rows alias the Q | K | V rows");
+        ops.push_back(fop_gemm(c->X, kD, kD, lw.tc_w1, lw.ln_ff_w, lw.ln_ff_b, nullptr, c->QKV, kFF, kFF, 1));
+        ops.push_back(fop_gemm(c->QKV, kFF, kFF, lw.tc_w2, nullptr, nullptr, c->X, c->X, kD, kD, 0));
         // vad reads the ar_channel output: a side task of the first op of cross layer 0 (which only reads X)
         if (l == 1 && c->head_kind == VAPB_HEAD_VAP) ops[first].f.side = FSIDE_VAD;
     }
@@ -669,12 +674,6 @@ int build_fused2(vapb_ctx* c) {
     DA2(c->X2l, R2 * kD);
     DA2(c->G1h, R2 * 1280);
     DA2(c->G1l, R2 * 1280);
-    DA2(c->O2h, R2 * kD);
-    DA2(c->O2l, R2 * kD);
-    DA2(c->Qc2h, R2 * kD);
-    DA2(c->Qc2l, R2 * kD);
-    DA2(c->H2h, R2 * kFF);
-    DA2(c->H2l, R2 * kFF);
 #undef DA2
     if (rc) return rc;
     struct Planes { CUtensorMap hi128, lo128, hi64, lo64, hi32, lo32; };      // box rows 128 / 64 (loads) and 32 (epilogue stores)
@@ -683,10 +682,15 @@ int build_fused2(vapb_ctx* c) {
                tc_encode_bf16_2d(&m.hi64, hi, R2, cols, 64, err) && tc_encode_bf16_2d(&m.lo64, lo, R2, cols, 64, err) &&
                tc_encode_bf16_2d(&m.hi32, hi, R2, cols, 32, err) && tc_encode_bf16_2d(&m.lo32, lo, R2, cols, 32, err);
     };
-    Planes mX, mG1, mO, mQc, mH;
-    if (!planes(c->X2h, c->X2l, kD, mX) || !planes(c->G1h, c->G1l, 1280, mG1) || !planes(c->O2h, c->O2l, kD, mO) ||
-        !planes(c->Qc2h, c->Qc2l, kD, mQc) || !planes(c->H2h, c->H2l, kFF, mH))
+    // ONE plane pair of 1 280 columns per row carries every intermediate of a layer (less footprint in L2 = fewer dead lines
+    // written back to HBM): [Q | K | V | K cross | V cross] of the fused projection; the attention writes O over the Q columns
+    // of its own heads (Q is in shared memory by then), the cross attention's Q projection and its O go to the same 256
+    // columns once the self-attention's projection has consumed them, and the FFN's hidden rows take columns 0..767
+    // (Q / K / V of the self attention are dead; the cross K / V columns are never touched).
+    Planes mX, mG1;
+    if (!planes(c->X2h, c->X2l, kD, mX) || !planes(c->G1h, c->G1l, 1280, mG1))
         return fail(c, VAPB_ECUDA, "stream kernel v2 tensor maps: %s", err.c_str());
+    const Planes &mO = mG1, &mQc = mG1, &mH = mG1;
     CUtensorMap mXf, mKVs, mKVc;           // fp32 store targets: residual stream; K | V rows of the pruned layer for the tail
     if (!tc_encode_f32_2d(&mXf, c->X2f, R2, kD, 32, err) || !tc_encode_f32_3d(&mKVs, c->QKV, (size_t)2 * c->max_batch, c->T, 512, 32, err) ||
         !tc_encode_f32_3d(&mKVc, c->KVc, (size_t)2 * c->max_batch, c->T, 512, 32, err))
@@ -710,7 +714,7 @@ int build_fused2(vapb_ctx* c) {
         memset(&o, 0, sizeof o);
         o.m[0] = Q.hi128; o.m[1] = Q.lo128; o.m[2] = mG1.hi64; o.m[3] = mG1.lo64; o.m[4] = mO.hi32; o.m[5] = mO.lo32;
         o.f.kind = F2_ATTN; o.f.qcol = qcol; o.f.kcol = kcol; o.f.vcol = vcol; o.f.slopes = slopes; o.f.sibling = sibling;
-        o.f.out_hi = c->O2h; o.f.out_lo = c->O2l; o.f.ld_out = kD;
+        o.f.out_hi = c->G1h; o.f.out_lo = c->G1l; o.f.ld_out = 1280;
         ops.push_back(o);
     };
     {
@@ -728,11 +732,11 @@ int build_fused2(vapb_ctx* c) {
         attn(mG1, 0, 256, 512, lw.sa.slopes, 0);
         gemm(mO, kD, lw.sa.tc_proj, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, kD, 0);
         if (lw.cross) {
-            gemm(mX, kD, v.qc, kD, F2_OUT_PLANES, kD, v.s_qc, v.c_qc, 0, &mQc, c->Qc2h, c->Qc2l, kD, 1);
+            gemm(mX, kD, v.qc, kD, F2_OUT_PLANES, kD, v.s_qc, v.c_qc, 0, &mQc, c->G1h, c->G1l, 1280, 1);
             attn(mQc, 0, 768, 1024, lw.slopes_c, 1);
             gemm(mO, kD, lw.tc_proj_c, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, kD, 0);
         }
-        gemm(mX, kD, v.w1, kFF, F2_OUT_PLANES, kFF, v.s_1, v.c_1, 1, &mH, c->H2h, c->H2l, kFF, 0);
+        gemm(mX, kD, v.w1, kFF, F2_OUT_PLANES, kFF, v.s_1, v.c_1, 1, &mH, c->G1h, c->G1l, 1280, 0);
         gemm(mH, kFF, lw.tc_w2, kD, F2_OUT_X, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, kD, 0);
     }
     {   // pruned last layer: window-wide K / V (self: LayerNorm folded, cross: raw rows) as fp32 rows for the newest-frame tail
