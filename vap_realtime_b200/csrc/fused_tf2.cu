@@ -262,7 +262,18 @@ __device__ __forceinline__ void load_acc_block(const Ctx2& c, uint32_t taddr, in
     }
 }
 
-// planes out (+ LayerNorm correction, + GELU): one 128-byte row per thread and plane through the staging tile
+// planes out (+ LayerNorm correction, + GELU).  One 32-column block at a time, ROLLED (the kernel is instruction-cache
+// sensitive): the block's hi / lo halves (64 bytes per row and plane) go through the two halves of the warp's staging tile
+// (SWIZZLE_64B boxes) and leave as two TMA stores; the engine reads them while the next block is loaded, corrected,
+// activated and split.
+__device__ __forceinline__ uint32_t stgh_addr(uint32_t base, int row, int chunk) { return base + (uint32_t)row * 64u + ((uint32_t)(chunk ^ ((row >> 1) & 3)) << 4); }
+__device__ __forceinline__ void stgh_put_row(uint32_t base, int lane, const uint32_t* w) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stgh_addr(base, lane, ch)), "r"(w[4 * ch]), "r"(w[4 * ch + 1]), "r"(w[4 * ch + 2]),
+                     "r"(w[4 * ch + 3])
+                     : "memory");
+}
 __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, const F2Fields& op, const Fused2Params& p, int gs) {
     const int q = c.warp & 3, hf = c.warp >> 2;
     const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
@@ -280,8 +291,7 @@ __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, con
         tc_fence_after();
         if (fine && s == 0) fine[1] = clock64();
         if (fine && s == ns - 1) fine[2] = clock64();
-        uint32_t H[32], L[32];
-#pragma unroll
+#pragma unroll 1
         for (int blk = 0; blk < 2; ++blk) {
             const int col = col0 + 32 * blk;
             float v[32];
@@ -290,12 +300,21 @@ __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, con
 #ifndef VAPB_F2_NOGELU
             if (op.act == 1) gelu_block(v);          // eight independent chains in flight (tc_ptx.cuh)
 #endif
+            uint32_t H[16], L[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[16 * blk + e], L[16 * blk + e]);
+            for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[e], L[e]);
+            stg_wait_read(c.lane);                   // the previous block's halves: read while this one was computed
+            stgh_put_row(stg, c.lane, H);
+            stgh_put_row(stg + kStgBytes / 2, c.lane, L);
+            fence_proxy_async();
+            __syncwarp();
+            if (c.lane == 0) {
+                F2_STORE_P(tma_store_2d(&gop->m[4], col, grow0, stg);)
+                F2_STORE_P(tma_store_2d(&gop->m[5], col, grow0, stg + kStgBytes / 2);)
+                tma_store_commit();
+            }
+            __syncwarp();
         }
-        stg_wait_read(c.lane);                                  // the previous subtile's lo plane: read while this one was computed
-        store_plane_rows<true>(stg, c.lane, H, &gop->m[4], col0, grow0);
-        store_plane_rows<false>(stg, c.lane, L, &gop->m[5], col0, grow0);
     }
     stores_done(c.lane);
     if (fine) fine[3] = clock64();

@@ -640,6 +640,23 @@ bool tc_encode_bf16_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, in
     return encode_plane(map, ptr, (int)rows, (int)cols, box_rows, err);
 }
 
+// half-width store box: 32 bf16 columns (64 bytes) x box_rows rows, SWIZZLE_64B
+bool tc_encode_bf16_2d_half(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err) {
+    EncodeTiledFn fn = get_encode_fn(err);
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        err = "cuTensorMapEncodeTiled (bf16 half box) failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
 bool tc_encode_f32_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err) {
     EncodeTiledFn fn = get_encode_fn(err);
     if (!fn) return false;

@@ -45,6 +45,7 @@ bool tc_prepare_workspace(TcWorkspace& ws, size_t max_a_elems, std::vector<void*
 
 // 2D tensor map over a row-major bf16 tensor [rows][cols] (cols contiguous): box {64 cols, box_rows}, 128 B swizzle.
 bool tc_encode_bf16_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err);
+bool tc_encode_bf16_2d_half(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err);
 
 // fp32 maps for TMA STORES out of 128 B-swizzled staging tiles: box {32 floats, box_rows [, 1]}
 bool tc_encode_f32_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err);
