@@ -186,12 +186,6 @@ __device__ __forceinline__ void stg_wait_read(int lane) {
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
 }
-// a thread's 64 packed bf16 pairs (32 words = the 128 bytes of one plane row) -> plane rows [row0, row0 + 32), columns [col, col + 64)
-template <bool WAIT>
-__device__ __forceinline__ void store_plane_rows(uint32_t stg, int lane, const uint32_t* w, const CUtensorMap* map, int col, int row0) {
-    stg_put_row(stg, lane, w);
-    stg_tma_store_2d<true, WAIT>(stg, lane, map, col, row0);
-}
 // end of an op: every store this warp issued is complete before the op barrier publishes the results
 __device__ __forceinline__ void stores_done(int lane) {
     if (lane == 0) tma_store_wait_all();
@@ -274,6 +268,21 @@ __device__ __forceinline__ void stgh_put_row(uint32_t base, int lane, const uint
                      "r"(w[4 * ch + 3])
                      : "memory");
 }
+// hi / lo halves of a 32 x 32 block -> the two halves of the warp's staging tile -> two TMA stores (no wait: the caller runs
+// stg_wait_read() before it touches the tile again)
+__device__ __forceinline__ void store_block_halves(uint32_t stg, int lane, const uint32_t* H, const uint32_t* L, const CUtensorMap* map_h,
+                                                   const CUtensorMap* map_l, int col, int row0) {
+    stgh_put_row(stg, lane, H);
+    stgh_put_row(stg + kStgBytes / 2, lane, L);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        F2_STORE_P(tma_store_2d(map_h, col, row0, stg);)
+        F2_STORE_P(tma_store_2d(map_l, col, row0, stg + kStgBytes / 2);)
+        tma_store_commit();
+    }
+    __syncwarp();
+}
 __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, const F2Fields& op, const Fused2Params& p, int gs) {
     const int q = c.warp & 3, hf = c.warp >> 2;
     const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
@@ -304,16 +313,7 @@ __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, con
 #pragma unroll
             for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[e], L[e]);
             stg_wait_read(c.lane);                   // the previous block's halves: read while this one was computed
-            stgh_put_row(stg, c.lane, H);
-            stgh_put_row(stg + kStgBytes / 2, c.lane, L);
-            fence_proxy_async();
-            __syncwarp();
-            if (c.lane == 0) {
-                F2_STORE_P(tma_store_2d(&gop->m[4], col, grow0, stg);)
-                F2_STORE_P(tma_store_2d(&gop->m[5], col, grow0, stg + kStgBytes / 2);)
-                tma_store_commit();
-            }
-            __syncwarp();
+            store_block_halves(stg, c.lane, H, L, &gop->m[4], &gop->m[5], col, grow0);
         }
     }
     stores_done(c.lane);
@@ -341,11 +341,10 @@ __device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Op* gop, const F2
         tc_fence_after();
         if (fine && s == 0) fine[1] = clock64();
         if (fine && s == ns - 1) fine[2] = clock64();
-        uint32_t H[32], L[32];
-#pragma unroll
+#pragma unroll 1
         for (int blk = 0; blk < 2; ++blk) {
             const int col = col0 + 32 * blk;
-            stg_wait_read(c.lane);                              // the store issued before this point has left the tile
+            stg_wait_read(c.lane);                              // the stores issued before this point have left the tile
 #pragma unroll
             for (int i = 0; i < 8; ++i) stg_put_co(stg, c.lane, i, rc[i]);
             __syncwarp();
@@ -371,12 +370,12 @@ __device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Op* gop, const F2
                 stg_put_row(stg, c.lane, vb);
             }
             stg_tma_store_2d<false, false>(stg, c.lane, &gop->m[6], col, grow0);   // fp32 residual stream (read while the planes are split)
+            uint32_t H[16], L[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[16 * blk + e], L[16 * blk + e]);
+            for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[e], L[e]);
+            stg_wait_read(c.lane);
+            store_block_halves(stg, c.lane, H, L, &gop->m[4], &gop->m[5], col, grow0);
         }
-        stg_wait_read(c.lane);
-        store_plane_rows<true>(stg, c.lane, H, &gop->m[4], col0, grow0);
-        store_plane_rows<false>(stg, c.lane, L, &gop->m[5], col0, grow0);
     }
     stores_done(c.lane);
     if (fine) fine[3] = clock64();
@@ -399,7 +398,7 @@ __device__ __noinline__ void epilogue_f32(const Ctx2& c, const F2Op* gop, const 
         tc_fence_after();
         if (fine && s == 0) fine[1] = clock64();
         if (fine && s == ns - 1) fine[2] = clock64();
-#pragma unroll
+#pragma unroll 1
         for (int blk = 0; blk < 2; ++blk) {
             const int col = col0 + 32 * blk;
             float v[32];
@@ -701,18 +700,17 @@ __device__ __noinline__ void attn_workers(const Ctx2& c, const F2Op* gop, const 
     // ---- O of head x, rows of quadrant q -> planes (64 columns = one 128-byte plane row per thread)
     f2wait(c.o_full(x), par, 9, c.oi);
     tc_fence_after();
-    uint32_t H[32], L[32];
-#pragma unroll
+    const int grow0 = c.b * 128 + 32 * q;
+#pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-        uint32_t raw[32];
+        uint32_t raw[32], H[16], L[16];
         tmem_ld32(tm_q + kTmO2 + 64u * x + 32u * half, raw);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) split2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1]), H[16 * half + e], L[16 * half + e]);
+        for (int e = 0; e < 16; ++e) split2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1]), H[e], L[e]);
+        stg_wait_read(c.lane);
+        store_block_halves(c.stg(), c.lane, H, L, &gop->m[4], &gop->m[5], head * 64 + 32 * half, grow0);
     }
     tc_fence_before();
-    const int grow0 = c.b * 128 + 32 * q;
-    store_plane_rows<true>(c.stg(), c.lane, H, &gop->m[4], head * 64, grow0);
-    store_plane_rows<false>(c.stg(), c.lane, L, &gop->m[5], head * 64, grow0);
     stores_done(c.lane);
 }
 
@@ -764,12 +762,14 @@ __device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int
             vb[u] = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane + 4));
         }
     }
+    if (c.fine && c.tid == 0) c.fine[1] = clock64() + (long long)(__float_as_uint(va[7].x) & 0u);      // debug stamp: the rows have arrived
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const int j = c.warp + u * kWorkers2;
         const float v8[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
         if (j != jnew) emit_row(p, grow0 + j, c.lane, v8);
     }
+    if (c.fine && c.tid == 0) c.fine[2] = clock64();                                                    // debug stamp: rows emitted
     if (c.r == 0 && c.tid == 0 && !c.ghost) p.tvalid[c.b] = c.t;
 }
 
@@ -826,6 +826,7 @@ __device__ __noinline__ void ds_tail_op(const Ctx2& c, const Fused2Params& p, in
             }
         emit_row(p, grow0 + (c.t - 1), c.lane, v8);
     }
+    if (c.fine && c.lane == 0) c.fine[3] = clock64();                                                   // debug stamp: newest frame done
 }
 
 // ============================== op loop ==============================

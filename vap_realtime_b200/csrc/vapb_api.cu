@@ -676,12 +676,11 @@ int build_fused2(vapb_ctx* c) {
     DA2(c->G1l, R2 * 1280);
 #undef DA2
     if (rc) return rc;
-    // box rows 128 / 64 (loads) and 32 (epilogue stores; "h": 32-column half boxes of the plane epilogue)
-    struct Planes { CUtensorMap hi128, lo128, hi64, lo64, hi32, lo32, hi32h, lo32h; };
+    // box rows 128 / 64 (loads: 64 columns, SWIZZLE_128B) and 32 (epilogue stores: 32-column half boxes, SWIZZLE_64B)
+    struct Planes { CUtensorMap hi128, lo128, hi64, lo64, hi32h, lo32h; };
     auto planes = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, size_t cols, Planes& m) {
         return tc_encode_bf16_2d(&m.hi128, hi, R2, cols, 128, err) && tc_encode_bf16_2d(&m.lo128, lo, R2, cols, 128, err) &&
                tc_encode_bf16_2d(&m.hi64, hi, R2, cols, 64, err) && tc_encode_bf16_2d(&m.lo64, lo, R2, cols, 64, err) &&
-               tc_encode_bf16_2d(&m.hi32, hi, R2, cols, 32, err) && tc_encode_bf16_2d(&m.lo32, lo, R2, cols, 32, err) &&
                tc_encode_bf16_2d_half(&m.hi32h, hi, R2, cols, 32, err) && tc_encode_bf16_2d_half(&m.lo32h, lo, R2, cols, 32, err);
     };
     // ONE plane pair of 1 280 columns per row carries every intermediate of a layer (less footprint in L2 = fewer dead lines
@@ -704,7 +703,7 @@ int build_fused2(vapb_ctx* c) {
         F2Op o;
         memset(&o, 0, sizeof o);
         o.m[0] = A.hi64; o.m[1] = A.lo64; o.m[2] = w.map_hi[0]; o.m[3] = w.map_lo[0];
-        if (out_mode == F2_OUT_X) { o.m[4] = mX.hi32; o.m[5] = mX.lo32; o.m[6] = mXf; }
+        if (out_mode == F2_OUT_X) { o.m[4] = mX.hi32h; o.m[5] = mX.lo32h; o.m[6] = mXf; }
         else if (out_mode == F2_OUT_F32) { o.m[4] = mKVs; o.m[5] = mKVc; }
         else { o.m[4] = out->hi32h; o.m[5] = out->lo32h; }
         o.f.kind = F2_GEMM; o.f.K = K; o.f.N = N; o.f.out_mode = out_mode; o.f.n_ln = n_ln; o.f.ln_s = ls; o.f.ln_c = lc; o.f.act = act;
@@ -714,7 +713,7 @@ int build_fused2(vapb_ctx* c) {
     auto attn = [&](const Planes& Q, int qcol, int kcol, int vcol, const float* slopes, int sibling) {
         F2Op o;
         memset(&o, 0, sizeof o);
-        o.m[0] = Q.hi128; o.m[1] = Q.lo128; o.m[2] = mG1.hi64; o.m[3] = mG1.lo64; o.m[4] = mO.hi32; o.m[5] = mO.lo32;
+        o.m[0] = Q.hi128; o.m[1] = Q.lo128; o.m[2] = mG1.hi64; o.m[3] = mG1.lo64; o.m[4] = mO.hi32h; o.m[5] = mO.lo32h;
         o.f.kind = F2_ATTN; o.f.qcol = qcol; o.f.kcol = kcol; o.f.vcol = vcol; o.f.slopes = slopes; o.f.sibling = sibling;
         o.f.out_hi = c->G1h; o.f.out_lo = c->G1l; o.f.ld_out = 1280;
         ops.push_back(o);
