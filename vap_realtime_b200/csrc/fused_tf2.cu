@@ -716,30 +716,44 @@ __device__ __noinline__ void attn_workers(const Ctx2& c, const F2Op* gop, const 
 
 // ============================== ring gather (+ downsample tail) ==============================
 // Channel r of the stream: X rows 64r + j = ring rows oldest first (vap_main.py:274-283), zero rows above t.  One warp per
-// row, a lane owns 8 consecutive floats: fp32 row, bf16 planes and the LayerNorm block statistics (4 lanes per block).
-__device__ __forceinline__ void emit_row(const Fused2Params& p, size_t grow, int lane, const float (&v8)[8]) {
-    *reinterpret_cast<float4*>(p.Xf + grow * kD + 8 * lane) = make_float4(v8[0], v8[1], v8[2], v8[3]);
-    *reinterpret_cast<float4*>(p.Xf + grow * kD + 8 * lane + 4) = make_float4(v8[4], v8[5], v8[6], v8[7]);
+// row; a lane owns floats [4 lane, 4 lane + 4) and [128 + 4 lane, 128 + 4 lane + 4), so that every load and store of the
+// warp is one contiguous run of full 32-byte sectors (lane-owns-8-consecutive-floats made every fp32 store a half-sector
+// write): fp32 row, bf16 planes and the LayerNorm block statistics (8 lanes per 32-column block, two blocks per lane).
+__device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b) { asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory"); }
+__device__ __forceinline__ void emit_row(const Fused2Params& p, size_t grow, int lane, const float4 a, const float4 b) {
+    float* xf = p.Xf + grow * kD + 4 * lane;
+    *reinterpret_cast<float4*>(xf) = a;
+    *reinterpret_cast<float4*>(xf + 128) = b;
     uint32_t h[4], l[4];
+    split2(a.x, a.y, h[0], l[0]);
+    split2(a.z, a.w, h[1], l[1]);
+    split2(b.x, b.y, h[2], l[2]);
+    split2(b.z, b.w, h[3], l[3]);
+    __nv_bfloat16* xh = p.Xh + grow * kD + 4 * lane;
+    __nv_bfloat16* xl = p.Xl + grow * kD + 4 * lane;
+    st_global_v2(xh, h[0], h[1]);
+    st_global_v2(xh + 128, h[2], h[3]);
+    st_global_v2(xl, l[0], l[1]);
+    st_global_v2(xl + 128, l[2], l[3]);
+    float s0 = (a.x + a.y) + (a.z + a.w), s1 = (b.x + b.y) + (b.z + b.w);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) split2(v8[2 * e], v8[2 * e + 1], h[e], l[e]);
-    st_global_v4(p.Xh + grow * kD + 8 * lane, h[0], h[1], h[2], h[3]);
-    st_global_v4(p.Xl + grow * kD + 8 * lane, l[0], l[1], l[2], l[3]);
-    float bs = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) bs += v8[i];
-    bs += __shfl_xor_sync(0xffffffffu, bs, 1);
-    bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-    const float bm = bs * (1.0f / 32.0f);
-    float bq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float d = v8[i] - bm;
-        bq = fmaf(d, d, bq);
+    for (int o = 1; o < 8; o <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     }
-    bq += __shfl_xor_sync(0xffffffffu, bq, 1);
-    bq += __shfl_xor_sync(0xffffffffu, bq, 2);
-    if ((lane & 3) == 0) *reinterpret_cast<float2*>(p.stats + grow * 16 + (lane >> 2) * 2) = make_float2(bm, bq);
+    const float m0 = s0 * (1.0f / 32.0f), m1 = s1 * (1.0f / 32.0f);
+    float q0 = 0.f, q1 = 0.f;
+    { float d; d = a.x - m0; q0 = fmaf(d, d, q0); d = a.y - m0; q0 = fmaf(d, d, q0); d = a.z - m0; q0 = fmaf(d, d, q0); d = a.w - m0; q0 = fmaf(d, d, q0); }
+    { float d; d = b.x - m1; q1 = fmaf(d, d, q1); d = b.y - m1; q1 = fmaf(d, d, q1); d = b.z - m1; q1 = fmaf(d, d, q1); d = b.w - m1; q1 = fmaf(d, d, q1); }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    }
+    if ((lane & 7) == 0) {
+        *reinterpret_cast<float2*>(p.stats + grow * 16 + (lane >> 3) * 2) = make_float2(m0, q0);
+        *reinterpret_cast<float2*>(p.stats + grow * 16 + (4 + (lane >> 3)) * 2) = make_float2(m1, q1);
+    }
 }
 
 __device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int id, int cnt) {
@@ -748,26 +762,28 @@ __device__ __noinline__ void gather_op(const Ctx2& c, const Fused2Params& p, int
     const size_t grow0 = (size_t)c.b * 128 + 64 * ch;
     const bool ds = p.ds_part != nullptr && !c.ghost;
     const int jnew = ds ? c.t - 1 : -1;
-    // the warp's 8 rows (warp + 8u): every load is in flight before the first row is emitted -- the ring comes from HBM
-    // (nothing has touched it since the previous step), and a row-at-a-time loop paid that latency four times over
-    float4 va[8], vb[8];
+    // The warp's 8 rows (warp + 8u), two at a time.  What paces this op is not the loop shape (8 rows in flight: the same
+    // 24 k cycles) but the stores: 128 KB per CTA at ~2 TB/s chip-wide, the rate at which L2 can evict dirty lines to make
+    // room (timing-only build without the stores: 15 k), and the tensor-map prefetch of the two idle warps (20-24 k).
+#pragma unroll 1
+    for (int u0 = 0; u0 < 8; u0 += 2) {
+        float4 va[2], vb[2];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int j = c.warp + u * kWorkers2;
-        va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[u] = va[u];
-        if (j < c.t && j != jnew) {
-            const int slot = (cnt - c.t + j) % p.T;
-            va[u] = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane));
-            vb[u] = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 8 * c.lane + 4));
+        for (int u = 0; u < 2; ++u) {
+            const int j = c.warp + (u0 + u) * kWorkers2;
+            va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[u] = va[u];
+            if (j < c.t && j != jnew) {
+                const int slot = (cnt - c.t + j) % p.T;
+                va[u] = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 4 * c.lane));
+                vb[u] = __ldg(reinterpret_cast<const float4*>(rg + (size_t)slot * kD + 128 + 4 * c.lane));
+            }
         }
-    }
-    if (c.fine && c.tid == 0) c.fine[1] = clock64() + (long long)(__float_as_uint(va[7].x) & 0u);      // debug stamp: the rows have arrived
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int j = c.warp + u * kWorkers2;
-        const float v8[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-        if (j != jnew) emit_row(p, grow0 + j, c.lane, v8);
+        for (int u = 0; u < 2; ++u) {
+            const int j = c.warp + (u0 + u) * kWorkers2;
+            if (j != jnew) emit_row(p, grow0 + j, c.lane, va[u], vb[u]);
+        }
     }
     if (c.fine && c.tid == 0) c.fine[2] = clock64();                                                    // debug stamp: rows emitted
     if (c.r == 0 && c.tid == 0 && !c.ghost) p.tvalid[c.b] = c.t;
@@ -781,7 +797,7 @@ __device__ __noinline__ void ds_tail_op(const Ctx2& c, const Fused2Params& p, in
     const bool ds = p.ds_part != nullptr && !c.ghost;
     if (ds) {
         const int n = 2 * c.b + ch;
-        const float* pr = p.ds_part + (size_t)n * kD + 8 * c.lane;
+        const float* pr = p.ds_part + (size_t)n * kD + 4 * c.lane;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
         for (int z0 = 0; z0 < p.ds_nsplit; z0 += 8) {
             float4 pa[8], pb[8];
@@ -789,7 +805,7 @@ __device__ __noinline__ void ds_tail_op(const Ctx2& c, const Fused2Params& p, in
             for (int u = 0; u < 8; ++u) {
                 const float* q8 = pr + (size_t)min(z0 + u, p.ds_nsplit - 1) * p.ds_stride;
                 pa[u] = __ldcg(reinterpret_cast<const float4*>(q8));
-                pb[u] = __ldcg(reinterpret_cast<const float4*>(q8 + 4));
+                pb[u] = __ldcg(reinterpret_cast<const float4*>(q8 + 128));
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -811,8 +827,8 @@ __device__ __noinline__ void ds_tail_op(const Ctx2& c, const Fused2Params& p, in
             sq = fmaf(d, d, sq);
         }
         const float rstd = 1.0f / sqrtf(warp_sum2(sq) * (1.0f / 256.0f) + 1e-5f);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.ds_lnw + 8 * c.lane)), w1 = __ldg(reinterpret_cast<const float4*>(p.ds_lnw + 8 * c.lane + 4));
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ds_lnb + 8 * c.lane)), g1 = __ldg(reinterpret_cast<const float4*>(p.ds_lnb + 8 * c.lane + 4));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.ds_lnw + 4 * c.lane)), w1 = __ldg(reinterpret_cast<const float4*>(p.ds_lnw + 128 + 4 * c.lane));
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ds_lnb + 4 * c.lane)), g1 = __ldg(reinterpret_cast<const float4*>(p.ds_lnb + 128 + 4 * c.lane));
         const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) v8[i] = gelu_erf((v8[i] - mean) * rstd * ww[i] + bb[i]);
@@ -821,10 +837,10 @@ __device__ __noinline__ void ds_tail_op(const Ctx2& c, const Fused2Params& p, in
 #pragma unroll
         for (int k = 0; k < 2; ++k)
             if (dst[k]) {
-                *reinterpret_cast<float4*>(dst[k] + 8 * c.lane) = o0;
-                *reinterpret_cast<float4*>(dst[k] + 8 * c.lane + 4) = o1;
+                *reinterpret_cast<float4*>(dst[k] + 4 * c.lane) = o0;
+                *reinterpret_cast<float4*>(dst[k] + 128 + 4 * c.lane) = o1;
             }
-        emit_row(p, grow0 + (c.t - 1), c.lane, v8);
+        emit_row(p, grow0 + (c.t - 1), c.lane, o0, o1);
     }
     if (c.fine && c.lane == 0) c.fine[3] = clock64();                                                   // debug stamp: newest frame done
 }
