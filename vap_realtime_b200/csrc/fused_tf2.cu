@@ -100,21 +100,6 @@ struct Ctx2 {
     __device__ __forceinline__ uint32_t tmem_slot() const { return misc() + 104u; }
 };
 
-// exact-erf GELU, erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7), as in fused_tf.cu
-__device__ __forceinline__ float gelu_as2(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float pl = fmaf(1.061405429f, t, -1.453152027f);
-    pl = fmaf(pl, t, 1.421413741f);
-    pl = fmaf(pl, t, -0.284496736f);
-    pl = fmaf(pl, t, 0.254829592f);
-    const float er = 1.0f - pl * t * __expf(-z * z);
-    return 0.5f * x + 0.5f * fabsf(x) * er;
-}
-
-__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 
 // timing experiments only (results are wrong): VAPB_F2_NOSTORE drops every epilogue store, _NOSTORE_P only the plane
 // stores, _NOSTORE_X only the fp32 stores; VAPB_F2_NOFENCE drops the proxy fence in front of the op barrier; VAPB_F2_NOGELU
@@ -147,13 +132,6 @@ __device__ __forceinline__ void stg_get_row(uint32_t stg, int lane, uint32_t* w)
                      : "memory");
 }
 // coalesced side: pass i covers rows 4i .. 4i + 3, 8 lanes x 16 bytes = the 128 bytes of one row
-__device__ __forceinline__ uint4 stg_get_co(uint32_t stg, int lane, int i) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"(stg_addr(stg, 4 * i + (lane >> 3), lane & 7))
-                 : "memory");
-    return v;
-}
 __device__ __forceinline__ void stg_put_co(uint32_t stg, int lane, int i, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_addr(stg, 4 * i + (lane >> 3), lane & 7)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");

@@ -479,7 +479,7 @@ k_lstm_recurrent(const float* __restrict__ Gx,      // [NC][n_steps][1024]  W_ih
     float* sC = sG + kLstmRT * kLstmGPitch;            // [RT][32]
     unsigned crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int row0 = (blockIdx.x >> 3) * kLstmRT;
 
     // W_hh slice -> smem, transposed to [k][col]: 128 columns x 64 float4 along k, 8 loads in flight per thread
