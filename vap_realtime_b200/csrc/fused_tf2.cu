@@ -149,12 +149,14 @@ __device__ __forceinline__ void stg_put_co(uint32_t stg, int lane, int i, uint4 
 #else
 #define F2_EAGER false
 #endif
+// Stores address [sequence][position][column]: the 32 rows of warp quadrant q of stream slot b are positions 32 (q & 1) ..
+// of sequence 2 b + (q >> 1); the maps end at position T, so the padding rows of a tile are clipped.
 template <bool PLANE, bool WAIT = true>
-__device__ __forceinline__ void stg_tma_store_2d(uint32_t stg, int lane, const CUtensorMap* map, int c0, int c1) {
+__device__ __forceinline__ void stg_tma_store_2d(uint32_t stg, int lane, const CUtensorMap* map, int c0, int pos0, int seq) {
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        if (PLANE) { F2_STORE_P(tma_store_2d(map, c0, c1, stg);) } else { F2_STORE(tma_store_2d(map, c0, c1, stg);) }
+        if (PLANE) { F2_STORE_P(tma_store_3d(map, c0, pos0, seq, stg);) } else { F2_STORE(tma_store_3d(map, c0, pos0, seq, stg);) }
         tma_store_commit();
         if (WAIT || F2_EAGER) tma_store_wait_read();
     }
@@ -249,14 +251,14 @@ __device__ __forceinline__ void stgh_put_row(uint32_t base, int lane, const uint
 // hi / lo halves of a 32 x 32 block -> the two halves of the warp's staging tile -> two TMA stores (no wait: the caller runs
 // stg_wait_read() before it touches the tile again)
 __device__ __forceinline__ void store_block_halves(uint32_t stg, int lane, const uint32_t* H, const uint32_t* L, const CUtensorMap* map_h,
-                                                   const CUtensorMap* map_l, int col, int row0) {
+                                                   const CUtensorMap* map_l, int col, int pos0, int seq) {
     stgh_put_row(stg, lane, H);
     stgh_put_row(stg + kStgBytes / 2, lane, L);
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        F2_STORE_P(tma_store_2d(map_h, col, row0, stg);)
-        F2_STORE_P(tma_store_2d(map_l, col, row0, stg + kStgBytes / 2);)
+        F2_STORE_P(tma_store_3d(map_h, col, pos0, seq, stg);)
+        F2_STORE_P(tma_store_3d(map_l, col, pos0, seq, stg + kStgBytes / 2);)
         tma_store_commit();
     }
     __syncwarp();
@@ -264,7 +266,6 @@ __device__ __forceinline__ void store_block_halves(uint32_t stg, int lane, const
 __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, const F2Fields& op, const Fused2Params& p, int gs) {
     const int q = c.warp & 3, hf = c.warp >> 2;
     const size_t grow = (size_t)c.b * 128 + 32 * q + c.lane;
-    const int grow0 = c.b * 128 + 32 * q;
     const int ns = op.N >> 8;
     const uint32_t tm_row = c.tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = c.stg();
@@ -291,7 +292,7 @@ __device__ __noinline__ void epilogue_planes(const Ctx2& c, const F2Op* gop, con
 #pragma unroll
             for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[e], L[e]);
             stg_wait_read(c.lane);                   // the previous block's halves: read while this one was computed
-            store_block_halves(stg, c.lane, H, L, &gop->m[4], &gop->m[5], col, grow0);
+            store_block_halves(stg, c.lane, H, L, &gop->m[4], &gop->m[5], col, 32 * (q & 1), 2 * c.b + (q >> 1));
         }
     }
     stores_done(c.lane);
@@ -347,12 +348,12 @@ __device__ __noinline__ void epilogue_x(const Ctx2& c, const F2Op* gop, const F2
                 for (int e = 0; e < 32; ++e) vb[e] = __float_as_uint(v[e]);
                 stg_put_row(stg, c.lane, vb);
             }
-            stg_tma_store_2d<false, false>(stg, c.lane, &gop->m[6], col, grow0);   // fp32 residual stream (read while the planes are split)
+            stg_tma_store_2d<false, false>(stg, c.lane, &gop->m[6], col, 32 * (q & 1), 2 * c.b + (q >> 1));   // fp32 residual stream (read while the planes are split)
             uint32_t H[16], L[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) split2(v[2 * e], v[2 * e + 1], H[e], L[e]);
             stg_wait_read(c.lane);
-            store_block_halves(stg, c.lane, H, L, &gop->m[4], &gop->m[5], col, grow0);
+            store_block_halves(stg, c.lane, H, L, &gop->m[4], &gop->m[5], col, 32 * (q & 1), 2 * c.b + (q >> 1));
         }
     }
     stores_done(c.lane);
@@ -678,7 +679,6 @@ __device__ __noinline__ void attn_workers(const Ctx2& c, const F2Op* gop, const 
     // ---- O of head x, rows of quadrant q -> planes (64 columns = one 128-byte plane row per thread)
     f2wait(c.o_full(x), par, 9, c.oi);
     tc_fence_after();
-    const int grow0 = c.b * 128 + 32 * q;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         uint32_t raw[32], H[16], L[16];
@@ -686,7 +686,7 @@ __device__ __noinline__ void attn_workers(const Ctx2& c, const F2Op* gop, const 
 #pragma unroll
         for (int e = 0; e < 16; ++e) split2(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1]), H[e], L[e]);
         stg_wait_read(c.lane);
-        store_block_halves(c.stg(), c.lane, H, L, &gop->m[4], &gop->m[5], head * 64 + 32 * half, grow0);
+        store_block_halves(c.stg(), c.lane, H, L, &gop->m[4], &gop->m[5], head * 64 + 32 * half, 32 * (q & 1), 2 * c.b + (q >> 1));
     }
     tc_fence_before();
     stores_done(c.lane);

@@ -657,6 +657,24 @@ bool tc_encode_bf16_2d_half(CUtensorMap* map, void* ptr, size_t rows, size_t col
     return true;
 }
 
+// the same half box over [sequence][position < n_pos][cols] with `seq_stride_rows` rows between sequences: rows of a box
+// at positions >= n_pos are clipped, i.e. never written
+bool tc_encode_bf16_3d_half(CUtensorMap* map, void* ptr, size_t n_seq, size_t n_pos, size_t cols, size_t seq_stride_rows, std::string& err) {
+    EncodeTiledFn fn = get_encode_fn(err);
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)n_pos, (cuuint64_t)n_seq};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * 2 * seq_stride_rows};
+    const cuuint32_t box[3] = {32u, 32u, 1u};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        err = "cuTensorMapEncodeTiled (bf16 half box, 3d) failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
 bool tc_encode_f32_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err) {
     EncodeTiledFn fn = get_encode_fn(err);
     if (!fn) return false;
@@ -672,11 +690,11 @@ bool tc_encode_f32_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int
     }
     return true;
 }
-bool tc_encode_f32_3d(CUtensorMap* map, void* ptr, size_t d2, size_t d1, size_t cols, int box_d1, std::string& err) {
+bool tc_encode_f32_3d(CUtensorMap* map, void* ptr, size_t d2, size_t d1, size_t cols, int box_d1, std::string& err, size_t d2_stride_rows) {
     EncodeTiledFn fn = get_encode_fn(err);
     if (!fn) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)d1, (cuuint64_t)d2};
-    const cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * d1};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * (d2_stride_rows ? d2_stride_rows : d1)};
     const cuuint32_t box[3] = {32u, (cuuint32_t)box_d1, 1u};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

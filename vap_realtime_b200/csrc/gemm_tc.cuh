@@ -49,7 +49,8 @@ bool tc_encode_bf16_2d_half(CUtensorMap* map, void* ptr, size_t rows, size_t col
 
 // fp32 maps for TMA STORES out of 128 B-swizzled staging tiles: box {32 floats, box_rows [, 1]}
 bool tc_encode_f32_2d(CUtensorMap* map, void* ptr, size_t rows, size_t cols, int box_rows, std::string& err);
-bool tc_encode_f32_3d(CUtensorMap* map, void* ptr, size_t d2, size_t d1, size_t cols, int box_d1, std::string& err);
+bool tc_encode_f32_3d(CUtensorMap* map, void* ptr, size_t d2, size_t d1, size_t cols, int box_d1, std::string& err, size_t d2_stride_rows = 0);
+bool tc_encode_bf16_3d_half(CUtensorMap* map, void* ptr, size_t n_seq, size_t n_pos, size_t cols, size_t seq_stride_rows, std::string& err);
 
 int tc_pick_ksplit(int M, int N, int K, int max_split);
 

@@ -676,12 +676,13 @@ int build_fused2(vapb_ctx* c) {
     DA2(c->G1l, R2 * 1280);
 #undef DA2
     if (rc) return rc;
-    // box rows 128 / 64 (loads: 64 columns, SWIZZLE_128B) and 32 (epilogue stores: 32-column half boxes, SWIZZLE_64B)
+    // box rows 128 / 64 (loads: 64 columns, SWIZZLE_128B) and 32 (epilogue stores: 32-column half boxes, SWIZZLE_64B, over
+    // [sequence][position < T][cols]: the padding rows T..63 of a sequence are clipped, never written, and stay zero)
     struct Planes { CUtensorMap hi128, lo128, hi64, lo64, hi32h, lo32h; };
     auto planes = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, size_t cols, Planes& m) {
         return tc_encode_bf16_2d(&m.hi128, hi, R2, cols, 128, err) && tc_encode_bf16_2d(&m.lo128, lo, R2, cols, 128, err) &&
                tc_encode_bf16_2d(&m.hi64, hi, R2, cols, 64, err) && tc_encode_bf16_2d(&m.lo64, lo, R2, cols, 64, err) &&
-               tc_encode_bf16_2d_half(&m.hi32h, hi, R2, cols, 32, err) && tc_encode_bf16_2d_half(&m.lo32h, lo, R2, cols, 32, err);
+               tc_encode_bf16_3d_half(&m.hi32h, hi, R2 / 64, c->T, cols, 64, err) && tc_encode_bf16_3d_half(&m.lo32h, lo, R2 / 64, c->T, cols, 64, err);
     };
     // ONE plane pair of 1 280 columns per row carries every intermediate of a layer (less footprint in L2 = fewer dead lines
     // written back to HBM): [Q | K | V | K cross | V cross] of the fused projection; the attention writes O over the Q columns
@@ -693,7 +694,7 @@ int build_fused2(vapb_ctx* c) {
         return fail(c, VAPB_ECUDA, "stream kernel v2 tensor maps: %s", err.c_str());
     const Planes &mO = mG1, &mQc = mG1, &mH = mG1;
     CUtensorMap mXf, mKVs, mKVc;           // fp32 store targets: residual stream; K | V rows of the pruned layer for the tail
-    if (!tc_encode_f32_2d(&mXf, c->X2f, R2, kD, 32, err) || !tc_encode_f32_3d(&mKVs, c->QKV, (size_t)2 * c->max_batch, c->T, 512, 32, err) ||
+    if (!tc_encode_f32_3d(&mXf, c->X2f, R2 / 64, c->T, kD, 32, err, 64) || !tc_encode_f32_3d(&mKVs, c->QKV, (size_t)2 * c->max_batch, c->T, 512, 32, err) ||
         !tc_encode_f32_3d(&mKVc, c->KVc, (size_t)2 * c->max_batch, c->T, 512, 32, err))
         return fail(c, VAPB_ECUDA, "stream kernel v2 tensor maps: %s", err.c_str());
 
