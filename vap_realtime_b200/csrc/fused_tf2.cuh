@@ -1,16 +1,21 @@
 // Per-stream persistent transformer kernel, second generation ("stream kernel v2"), T <= 64.
 //
-// Same ownership as fused_tf.cuh (a cluster of two CTAs owns one stereo stream for the whole stack; the M = 128 tile is
-// both channels of the stream, sequence c in tile rows 64c .. 64c + T - 1; CTA r computes output columns
-// 256 j + 128 r .. + 127 of every GEMM, i.e. heads 2r, 2r + 1 of every projection), but every operand now reaches the
-// tensor core the standard way -- TMA -> shared memory -> tcgen05.mma -- and every conversion happens ONCE, in the
-// epilogue of the op that produces a tensor:
+// A cluster of FOUR CTAs owns two stereo streams for the whole stack: CTA (stream slot s, column half r).  The M = 128 tile
+// of a stream is both of its channels (sequence c in tile rows 64c .. 64c + T - 1); CTA r computes output columns
+// 256 j + 128 r .. + 127 of every GEMM, i.e. heads 2r, 2r + 1 of every projection.  Every operand reaches the tensor core
+// the standard way -- TMA -> shared memory -> tcgen05.mma -- and every conversion happens ONCE, in the epilogue of the op
+// that produces a tensor:
 //
-//   * activations live in L2 as bf16 hi / lo planes in tile-row layout ([batch * 128 rows][cols]); the epilogue of the
-//     producing op writes them thread-per-row straight out of tensor memory (no shared-memory transpose), the consuming
-//     op fetches 128 x 64 tiles with TMA (128 B swizzle).  No register staging, no A operand in tensor memory: all 512
-//     TMEM columns are accumulators (4 x 128 columns), so MMAs are 128 x 128 x 16 and two accumulators are always
-//     issued interleaved;
+//   * activations live in L2 as bf16 hi / lo planes in tile-row layout ([slot * 128 rows][cols]); the consuming op fetches
+//     128 x 64 tiles with TMA (128 B swizzle), the two CTAs of a stream each multicast half of every A tile, the two CTAs of
+//     a column half each multicast half of every W tile.  All 512 TMEM columns are accumulators (4 x 128): pairs of
+//     subtiles are issued interleaved, a single subtile as one chain of N = 128 MMAs;
+//   * the epilogue of the producing op writes the planes: tensor memory hands a thread one row, the rows of a 32-column
+//     block pass through the warp's staging tile (two SWIZZLE_64B half tiles: hi, lo) and leave as TMA stores whose maps
+//     are [sequence][position < T][cols], so the padding rows of a tile are never written;
+//   * ONE 1 280-column scratch row per tile row carries every intermediate of a layer ([Q | K | V | K_c | V_c], the
+//     attention output over the Q columns, the cross attention's Q and output, the FFN hidden rows): the working set of
+//     64 streams fits L2;
 //   * LayerNorm moved from the prologue to the epilogue: the GEMM runs on the RAW rows with weights pre-scaled by the
 //     LayerNorm gain, y_n = rstd * (x (W o g)^T - mu * s_n) + c_n with s_n = sum_k g_k W_nk, c_n = sum_k b_k W_nk
 //     (emulated on the checkpoint: tools/emulate_rawln.py, 1.5e-6 vs 1.1e-6 for normalise-then-split).  Row statistics
@@ -18,6 +23,7 @@
 //     operand therefore serves the self-attention Q/K/V projection AND the cross-attention K/V projection of a layer
 //     (one op, N = 1280);
 //   * the residual stream X is kept in fp32 next to its planes; the epilogue of proj / FFN2 adds it thread-per-row;
+//   * the window-wide K / V of the pruned last layer leave as fp32 rows (F2_OUT_F32) for the newest-frame tail (k_tail);
 //   * ops whose inputs were produced by the same CTA (attention after its projections) are separated by a CTA
 //     barrier instead of a cluster barrier.
 #pragma once
@@ -56,8 +62,8 @@ struct alignas(64) F2Op {
     // GEMM: m[0] / m[1] = A hi / lo planes (box 64 rows x 64: each CTA of a stream multicasts half a tile),
     //       m[2] / m[3] = W hi / lo (box 64 n x 64 k: each CTA of a column half multicasts half a tile)
     // ATTN: m[0] / m[1] = Q planes (box 128 rows x 64), m[2] / m[3] = K / V planes (box 64 rows x 64)
-    // every op: m[4] / m[5] = output hi / lo planes (box 32 rows x 64 columns, TMA stores out of the epilogue staging tiles);
-    //           F2_OUT_X: the X planes, m[6] = the fp32 residual stream (box 32 rows x 32 floats);
+    // every op: m[4] / m[5] = output hi / lo planes, [sequence][position < T][cols], box 1 x 32 x 32 columns (SWIZZLE_64B half tiles);
+    //           F2_OUT_X: the X planes, m[6] = the fp32 residual stream, same 3-D shape, box 1 x 32 x 32 floats;
     //           F2_OUT_F32: m[4] / m[5] = fp32 [sequence][position][512] tensors of out_f / out_f2 (box 32 x 32 x 1: positions >= T are clipped)
     CUtensorMap m[7];
     F2Fields f;
