@@ -1,25 +1,27 @@
 // Per-stream persistent transformer kernel, second generation -- see fused_tf2.cuh for the scheme.
 //
-// Cluster of FOUR CTAs = two streams x two column halves (rank k: stream slot k >> 1, half r = k & 1).  The kernel is bound
-// by the SM <-> L2 fabric (every CTA streams its half of every weight matrix for every stream), so both operand streams
-// are multicast: the two CTAs of a stream share every A tile (each issues 64 of its 128 rows to both), the two CTAs with
+// Cluster of FOUR CTAs = two streams x two column halves (rank k: stream slot k >> 1, half r = k & 1).  Every CTA needs its
+// half of every weight matrix for every stream, so both operand streams are multicast (this halves the L2 -> SM traffic;
+// it did not change the run time: the fabric is not the limiter): the two CTAs of a stream share every A tile (each issues 64 of its 128 rows to both), the two CTAs with
 // the same half r share every W tile across the two streams (each issues 64 of its 128 rows to both).  "Empty" barriers
 // therefore collect one tcgen05.commit from each of the two consumers.  An odd batch gets a ghost stream that runs the
 // same pipeline on scratch rows and writes no state.
 //
 // CTA anatomy (384 threads, 1 CTA per SM):
-//   warps 0-7  workers: GEMM epilogues (tcgen05.ld -> LayerNorm correction / GELU / residual -> bf16 hi / lo planes,
-//              thread-per-row, straight to global), softmax, ring gather
+//   warps 0-7  workers: GEMM epilogues (tcgen05.ld -> LayerNorm correction / GELU / residual -> bf16 hi / lo planes ->
+//              staging tile -> TMA store), softmax, ring gather
 //   warp 8     TMA producer of the W tiles; weights are constants, so it runs AHEAD of the op barriers (throttled only by
 //              the ring): the first W tiles of an op are in shared memory before the barrier in front of it opens
 //   warp 9     TMEM owner + the single thread that issues tcgen05.mma
 //   warp 10    TMA producer of everything that depends on the previous op: A tiles; Q / K / V tiles of the attention
-//   warp 11    side tasks (vad, newest-frame gather)
+//              (warps 9 and 10 prefetch every op's tensor maps while the ring is gathered)
+//   warp 11    side tasks (newest embedding of the ring gather, vad, newest-frame gather)
 // Every stage holds the hi and the lo plane of one 128 x 64 bf16 tile (2 x 16 KB, 128 B swizzle): an A ring (A tiles
 // stream once per subtile group; Q of the attention) and a W ring (W tiles; K and V of the attention at reserved ring
-// positions).  Each worker warp owns a 4 KB staging tile through which every global access of the epilogue is
-// transposed: tensor memory hands a thread one ROW, but a warp-wide access that touches 32 different 128 B lines costs
-// the LSU 32 passes (measured: thread-per-row stores made the first cut of this kernel slower than its predecessor).
+// positions).  Each worker warp owns a 4 KB staging tile through which every global access of the epilogue passes:
+// tensor memory hands a thread one ROW, but a warp-wide access that touches 32 different 128 B lines costs the LSU 32
+// passes (measured: thread-per-row stores made the first cut of this kernel slower than its predecessor), so the rows
+// are written into the tile in the TMA box layout and leave as TMA stores.
 // All pipelines carry their phase across ops through running counters that every role advances identically.
 #include "fused_tf2.cuh"
 #include "tc_ptx.cuh"
